@@ -1,0 +1,1 @@
+"""Stub package: test infrastructure only (see oracle/README.md)."""
