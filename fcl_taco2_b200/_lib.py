@@ -1,0 +1,123 @@
+"""ctypes binding of the C ABI in include/fcl_taco2.h (libfcl_taco2.so).
+
+This is the thin custom-op layer: PyTorch only supplies device memory
+(`tensor.data_ptr()`) and the current stream. There is no CPU fallback -- if the
+shared library is missing, loading raises with the build command.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
+ABI_VERSION = 3
+
+i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
+ptr = C.c_void_p
+
+
+class LenRegParams(C.Structure):
+    _fields_ = [("n_rows", i32), ("n_utts", i32), ("dur", ptr), ("utt_off", ptr), ("frame_off", ptr),
+                ("utt_frame_off", ptr), ("order", ptr), ("totals", ptr)]
+
+
+class FrameMapParams(C.Structure):
+    _fields_ = [("n_rows", i32), ("n_utts", i32), ("n_frames", i32), ("frame_off", ptr), ("utt_frame_off", ptr),
+                ("frame_row", ptr), ("frame_step", ptr), ("frame_seg_lo", ptr), ("frame_seg_hi", ptr),
+                ("position", ptr)]
+
+
+class ConvGemmParams(C.Structure):
+    _fields_ = [("rows", i32), ("cin", i32), ("cout", i32), ("taps", i32), ("a", ptr), ("lda", i32),
+                ("gather", ptr), ("seg_lo", ptr), ("seg_hi", ptr), ("w", ptr), ("bias", ptr), ("residual", ptr),
+                ("ldr", i32), ("out", ptr), ("ldo", i32), ("act", i32)]
+
+
+class LayerNormParams(C.Structure):
+    _fields_ = [("rows", i32), ("chans", i32), ("x", ptr), ("gamma", ptr), ("beta", ptr), ("y", ptr),
+                ("head_w", ptr), ("head_b", f32), ("head_out", ptr), ("dur_out", ptr)]
+
+
+class EmbedAddParams(C.Structure):
+    _fields_ = [("rows", i32), ("chans", i32), ("taps", i32), ("h", ptr), ("pitch", ptr), ("energy", ptr),
+                ("seg_lo", ptr), ("seg_hi", ptr), ("wp", ptr), ("bp", ptr), ("we", ptr), ("be", ptr), ("hn", ptr)]
+
+
+class BiLstmParams(C.Structure):
+    _fields_ = [("n_utts", i32), ("hidden", i32), ("utt_off", ptr), ("gx", ptr), ("whh", ptr), ("out", ptr),
+                ("group", i32)]
+
+
+class DecoderParams(C.Structure):
+    _fields_ = [("n_rows", i32), ("eunits", i32), ("dunits", i32), ("prenet_units", i32), ("odim", i32),
+                ("order", ptr), ("dur", ptr), ("frame_off", ptr), ("row_utt", ptr), ("row_phone", ptr),
+                ("g0h", ptr), ("y0h", ptr), ("wp0", ptr), ("bp0", ptr), ("wp1", ptr), ("bp1", ptr),
+                ("w0", ptr), ("wpos", ptr), ("w1", ptr), ("b1", ptr), ("wf", ptr), ("cstate", ptr), ("before", ptr),
+                ("zoneout", f32), ("dropout_p", f32), ("dropout_seed", u64), ("tile_rows", i32)]
+
+
+STRUCTS = [LenRegParams, FrameMapParams, ConvGemmParams, LayerNormParams, EmbedAddParams, BiLstmParams,
+           DecoderParams]
+
+ENTRY_POINTS = {
+    "fcl_len_reg_scan": LenRegParams,
+    "fcl_len_reg_frame_map": FrameMapParams,
+    "fcl_conv_gemm_f32": ConvGemmParams,
+    "fcl_layernorm_f32": LayerNormParams,
+    "fcl_embed_add_f32": EmbedAddParams,
+    "fcl_bilstm_f32": BiLstmParams,
+    "fcl_decoder_f32": DecoderParams,
+}
+PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_last_error", "fcl_sm_count", "fcl_struct_size"]
+
+ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+MAX_DURATION = 1023
+
+
+class FclError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libfcl_taco2.so once; verify ABI version and struct layouts."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FclError(
+            f"{LIB_PATH} not found: the B200 path has no CPU fallback. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc, sm_100a).")
+    lib = C.CDLL(LIB_PATH)
+    lib.fcl_abi_version.restype = C.c_int
+    lib.fcl_last_error.restype = C.c_char_p
+    lib.fcl_sm_count.restype = C.c_int
+    lib.fcl_struct_size.restype = C.c_int
+    lib.fcl_struct_size.argtypes = [C.c_int]
+    if lib.fcl_abi_version() != ABI_VERSION:
+        raise FclError(f"ABI mismatch: library {lib.fcl_abi_version()} != binding {ABI_VERSION}; rebuild")
+    for i, st in enumerate(STRUCTS):
+        if lib.fcl_struct_size(i) != C.sizeof(st):
+            raise FclError(f"struct layout mismatch for {st.__name__}: C {lib.fcl_struct_size(i)} != ctypes {C.sizeof(st)}")
+    for name, st in ENTRY_POINTS.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(st), C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def call(name: str, params, stream: int):
+    """Invoke an entry point; raise FclError with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(C.byref(params), C.c_void_p(stream))
+    if rc != 0:
+        raise FclError(f"{name} failed ({rc}): {lib.fcl_last_error().decode()}")
+
+
+def dptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

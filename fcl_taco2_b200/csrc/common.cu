@@ -1,0 +1,48 @@
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace fcl {
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return FCL_ECUDA;
+  }
+  return FCL_OK;
+}
+}  // namespace fcl
+
+extern "C" int fcl_abi_version(void) { return FCL_ABI_VERSION; }
+extern "C" const char* fcl_last_error(void) { return fcl::g_err; }
+extern "C" int fcl_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    fcl::set_error("fcl_sm_count: %s", cudaGetErrorString(cudaGetLastError()));
+    return FCL_ECUDA;
+  }
+  return n;
+}
+
+// ABI self-check for foreign-language bindings: sizeof of every parameter struct.
+extern "C" int fcl_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(FclLenRegParams);
+    case 1: return (int)sizeof(FclFrameMapParams);
+    case 2: return (int)sizeof(FclConvGemmParams);
+    case 3: return (int)sizeof(FclLayerNormParams);
+    case 4: return (int)sizeof(FclEmbedAddParams);
+    case 5: return (int)sizeof(FclBiLstmParams);
+    case 6: return (int)sizeof(FclDecoderParams);
+    default: return -1;
+  }
+}

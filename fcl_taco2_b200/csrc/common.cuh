@@ -1,0 +1,53 @@
+// Shared helpers of the FCL-taco2 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/fcl_taco2.h"
+
+namespace fcl {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define FCL_REQUIRE(cond, msg)                                                   \
+  do {                                                                           \
+    if (!(cond)) { ::fcl::set_error("%s: %s", __func__, msg); return FCL_EINVAL; } \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---- Philox4x32-10 (Salmon et al. SC'11); CPU twin: oracle/philox.py ------------------------
+struct Philox4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                  uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+// keep decisions of prenet units 4*quad .. 4*quad+3 for (utt, phoneme, step, layer)
+__device__ __forceinline__ Philox4 dropout_words(uint64_t seed, uint32_t utt, uint32_t phoneme,
+                                                  uint32_t step, uint32_t layer, uint32_t quad) {
+  return philox4x32_10(quad, (step & 0xFFFFFFu) | (layer << 24), phoneme, utt,
+                       (uint32_t)(seed & 0xFFFFFFFFull), (uint32_t)(seed >> 32));
+}
+
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  t = t + 0.5;                       // round half up == Python round() except exact .5 ties (p is a config constant)
+  if (t >= 4294967295.0) return 4294967295u;
+  if (t <= 0.0) return 0u;
+  return (uint32_t)t;
+}
+
+}  // namespace fcl

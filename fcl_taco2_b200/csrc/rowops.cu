@@ -1,0 +1,137 @@
+// Row-wise kernels of the variance/duration predictors and the pitch/energy embedding add.
+//   fcl_layernorm_f32 : espnet LayerNorm over channels (eps 1e-12) + optional Linear(C,1) head
+//                       + optional duration rounding (variance_predictor.py:62,66,90; espnet
+//                       DurationPredictor.inference, un-vendored).
+//   fcl_embed_add_f32 : Conv1d(1,E,k9) of the predicted pitch / energy + add to h
+//                       (e2e_tts_tacotron2_sa.py:435-443,657-658; decoder_sa.py:570-571).
+// HBM-bound: one warp per row, float4 accesses.
+#include "common.cuh"
+
+namespace fcl {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int kLnMaxPerLane = 8;   // float4 per lane: chans <= 32*4*8 = 1024
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(FclLayerNormParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int c4 = p.chans >> 2;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < p.rows; r += gridDim.x * warps_per_block) {
+    const float4* x = reinterpret_cast<const float4*>(p.x + (size_t)r * p.chans);
+    float4 v[kLnMaxPerLane];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+      const int c = lane + i * 32;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < c4) { v[i] = __ldg(x + c); s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+    }
+    const float mean = warp_sum(s) / (float)p.chans;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+      const int c = lane + i * 32;
+      if (c < c4) {
+        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (cc * cc + d * d);
+      }
+    }
+    const float var = warp_sum(q) / (float)p.chans;       // biased variance (torch layer_norm)
+    const float rstd = 1.0f / sqrtf(var + 1e-12f);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+      const int c = lane + i * 32;
+      if (c < c4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma) + c);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta) + c);
+        float4 y;
+        y.x = (v[i].x - mean) * rstd * g.x + b.x;
+        y.y = (v[i].y - mean) * rstd * g.y + b.y;
+        y.z = (v[i].z - mean) * rstd * g.z + b.z;
+        y.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (p.y) reinterpret_cast<float4*>(p.y + (size_t)r * p.chans)[c] = y;
+        if (p.head_w) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(p.head_w) + c);
+          dot += (y.x * w.x + y.y * w.y) + (y.z * w.z + y.w * w.w);
+        }
+      }
+    }
+    if (p.head_w) {
+      dot = warp_sum(dot) + p.head_b;
+      if (lane == 0) {
+        if (p.head_out) p.head_out[r] = dot;
+        if (p.dur_out) {
+          // clamp(round_half_even(exp(x) - 1), 0, cap); rintf rounds half to even like torch.round
+          float d = rintf(expf(dot) - 1.0f);
+          d = fminf(fmaxf(d, 0.f), (float)FCL_MAX_DURATION);
+          p.dur_out[r] = (int)d;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+embed_add_kernel(FclEmbedAddParams p) {
+  // one thread per (row, 4 channels)
+  const int c4 = p.chans >> 2;
+  const size_t total = (size_t)p.rows * c4;
+  const int half = p.taps >> 1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c4), c = (int)(i - (size_t)r * c4) * 4;
+    const int lo = p.seg_lo[r], hi = p.seg_hi[r];
+    float4 acc = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)r * p.chans + c));
+    float ap[4] = {0.f, 0.f, 0.f, 0.f}, ae[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < p.taps; ++j) {
+      const int src = r + j - half;
+      if (src < lo || src >= hi) continue;
+      const float pv = __ldg(p.pitch + src), ev = __ldg(p.energy + src);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ap[k] = fmaf(__ldg(p.wp + (size_t)(c + k) * p.taps + j), pv, ap[k]);
+        ae[k] = fmaf(__ldg(p.we + (size_t)(c + k) * p.taps + j), ev, ae[k]);
+      }
+    }
+    const float4 bp = __ldg(reinterpret_cast<const float4*>(p.bp + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(p.be + c));
+    // same association as the reference: (h + p_emb) + e_emb, embeds carry their bias
+    acc.x = (acc.x + (ap[0] + bp.x)) + (ae[0] + be.x);
+    acc.y = (acc.y + (ap[1] + bp.y)) + (ae[1] + be.y);
+    acc.z = (acc.z + (ap[2] + bp.z)) + (ae[2] + be.z);
+    acc.w = (acc.w + (ap[3] + bp.w)) + (ae[3] + be.w);
+    *reinterpret_cast<float4*>(p.hn + (size_t)r * p.chans + c) = acc;
+  }
+}
+
+}  // namespace fcl
+
+extern "C" int fcl_layernorm_f32(const FclLayerNormParams* p, void* stream) {
+  using namespace fcl;
+  FCL_REQUIRE(p && p->x && p->gamma && p->beta, "null pointer");
+  FCL_REQUIRE(p->rows > 0 && p->chans > 0 && p->chans % 4 == 0 && p->chans <= 128 * kLnMaxPerLane, "bad sizes");
+  int sms = fcl_sm_count();
+  if (sms < 0) return sms;
+  int blocks = min((p->rows + 7) / 8, sms * 8);
+  layernorm_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*p);
+  return check_launch("fcl_layernorm_f32");
+}
+
+extern "C" int fcl_embed_add_f32(const FclEmbedAddParams* p, void* stream) {
+  using namespace fcl;
+  FCL_REQUIRE(p && p->h && p->pitch && p->energy && p->seg_lo && p->seg_hi && p->wp && p->bp && p->we && p->be && p->hn,
+              "null pointer");
+  FCL_REQUIRE(p->rows > 0 && p->chans % 4 == 0 && (p->taps & 1), "bad sizes");
+  int sms = fcl_sm_count();
+  if (sms < 0) return sms;
+  size_t total = (size_t)p->rows * (p->chans / 4);
+  int blocks = (int)min((total + 255) / 256, (size_t)sms * 8);
+  embed_add_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*p);
+  return check_launch("fcl_embed_add_f32");
+}

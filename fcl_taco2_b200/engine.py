@@ -1,0 +1,237 @@
+"""Device-side orchestration of one batched `inference()` pass.
+
+Python only sequences kernel launches through the C ABI (fcl_taco2_b200._lib);
+torch supplies device memory and the stream. Every arithmetic step is a kernel
+of libfcl_taco2.so -- there is no torch op on activations and no CPU fallback.
+
+Pass order (reference: nets/teacher_training/e2e_tts_tacotron2_sa.py:624-683):
+  encoder convs (embedding gather fused) -> BiLSTM -> duration/pitch/energy predictors
+  -> pitch/energy embed add -> length regulator -> decoder (hoisted terms, persistent loop)
+  -> frame map -> postnet (+ residual).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, dptr
+from .hparams import HParams
+from .plan import BatchPlan
+
+
+@dataclass
+class BatchResult:
+    out: torch.Tensor                  # (F, odim) fp32, frames of all utterances in processing order
+    utt_frame_off: np.ndarray          # (B+1) frame offsets in processing order (host)
+    perm: np.ndarray                   # processing order -> caller index
+    extras: dict = field(default_factory=dict)
+
+    def per_utterance(self):
+        """-> list of (L_i, odim) views in the caller's order."""
+        outs = [None] * len(self.perm)
+        for k, i in enumerate(self.perm):
+            outs[int(i)] = self.out[int(self.utt_frame_off[k]): int(self.utt_frame_off[k + 1])]
+        return outs
+
+
+class Engine:
+    def __init__(self, hp: HParams, packed: dict, device, precision: str = "fp32"):
+        hp.validate()
+        if precision not in ("fp32",):
+            raise ValueError(f"unknown precision {precision!r}")
+        self.hp, self.precision = hp, precision
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.FclError("the B200 path runs on CUDA devices only (no CPU fallback)")
+        _lib.load()
+        self.w = {k: v.to(self.device) for k, v in packed.items()}
+        self.head_b = {s: float(packed[f"{s}_head_b"][0]) for s in ("dur", "pitch", "energy")}
+        self.launches = 0
+
+    # ------------------------------------------------------------------ launch helpers
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _call(self, name, params):
+        _lib.call(name, params, self._stream())
+        self.launches += 1
+
+    def conv_gemm(self, a, w, bias, rows, cin, cout, taps, act, seg=None, gather=None, residual=None, out=None,
+                  lda=None):
+        if out is None:
+            out = torch.empty((rows, cout), dtype=torch.float32, device=self.device)
+        p = _lib.ConvGemmParams(rows=rows, cin=cin, cout=cout, taps=taps, a=dptr(a), lda=lda or cin,
+                                gather=dptr(gather), seg_lo=dptr(seg[0]) if seg else None,
+                                seg_hi=dptr(seg[1]) if seg else None, w=dptr(w), bias=dptr(bias),
+                                residual=dptr(residual), ldr=cout, out=dptr(out), ldo=cout, act=act)
+        self._call("fcl_conv_gemm_f32", p)
+        return out
+
+    def layernorm(self, x, g, b, y=None, head_w=None, head_b=0.0, head_out=None, dur_out=None):
+        rows, chans = x.shape
+        p = _lib.LayerNormParams(rows=rows, chans=chans, x=dptr(x), gamma=dptr(g), beta=dptr(b), y=dptr(y),
+                                 head_w=dptr(head_w), head_b=head_b, head_out=dptr(head_out), dur_out=dptr(dur_out))
+        self._call("fcl_layernorm_f32", p)
+
+    # ------------------------------------------------------------------ stages
+    def encoder(self, ids, utt_off, seg, n_utts):
+        hp, w = self.hp, self.w
+        P, E = ids.shape[0], hp.eunits
+        x = self.conv_gemm(w["embed"], w["enc_conv0_w"], w["enc_conv0_b"], P, hp.embed_dim, hp.econv_chans, 5,
+                           ACT_RELU, seg=seg, gather=ids)
+        x = self.conv_gemm(x, w["enc_conv1_w"], w["enc_conv1_b"], P, hp.econv_chans, hp.econv_chans, 5, ACT_RELU, seg=seg)
+        x = self.conv_gemm(x, w["enc_conv2_w"], w["enc_conv2_b"], P, hp.econv_chans, hp.econv_chans, 5, ACT_RELU, seg=seg)
+        gx = self.conv_gemm(x, w["blstm_wih"], w["blstm_b"], P, hp.econv_chans, 4 * E, 1, ACT_NONE)
+        h = torch.empty((P, E), dtype=torch.float32, device=self.device)
+        p = _lib.BiLstmParams(n_utts=n_utts, hidden=E // 2, utt_off=dptr(utt_off), gx=dptr(gx), whh=dptr(w["blstm_whh"]),
+                              out=dptr(h), group=8 if n_utts >= 8 else 1)
+        self._call("fcl_bilstm_f32", p)
+        return h
+
+    def predictor(self, name, h, seg, want_dur=False):
+        """variance_predictor.py:86-93 / espnet DurationPredictor. -> (head (P,), dur int32 (P,) or None)"""
+        hp, w = self.hp, self.w
+        P, C = h.shape[0], hp.predictor_chans
+        x = self.conv_gemm(h, w[f"{name}_conv0_w"], w[f"{name}_conv0_b"], P, hp.eunits, C, 3, ACT_RELU, seg=seg)
+        self.layernorm(x, w[f"{name}_ln0_g"], w[f"{name}_ln0_b"], y=x)
+        x = self.conv_gemm(x, w[f"{name}_conv1_w"], w[f"{name}_conv1_b"], P, C, C, 3, ACT_RELU, seg=seg)
+        head = torch.empty((P,), dtype=torch.float32, device=self.device)
+        dur = torch.empty((P,), dtype=torch.int32, device=self.device) if want_dur else None
+        self.layernorm(x, w[f"{name}_ln1_g"], w[f"{name}_ln1_b"], head_w=w[f"{name}_head_w"],
+                       head_b=self.head_b[name], head_out=head, dur_out=dur)
+        return head, dur
+
+    def embed_add(self, h, pitch, energy, seg):
+        hp, w = self.hp, self.w
+        hn = torch.empty_like(h)
+        p = _lib.EmbedAddParams(rows=h.shape[0], chans=hp.eunits, taps=hp.embed_kernel, h=dptr(h), pitch=dptr(pitch),
+                                energy=dptr(energy), seg_lo=dptr(seg[0]), seg_hi=dptr(seg[1]), wp=dptr(w["pemb_w"]),
+                                bp=dptr(w["pemb_b"]), we=dptr(w["eemb_w"]), be=dptr(w["eemb_b"]), hn=dptr(hn))
+        self._call("fcl_embed_add_f32", p)
+        return hn
+
+    def len_reg_scan(self, dur, utt_off, n_utts):
+        P = dur.shape[0]
+        dev = self.device
+        frame_off = torch.empty((P + 1,), dtype=torch.int32, device=dev)
+        utt_frame_off = torch.empty((n_utts + 1,), dtype=torch.int32, device=dev)
+        order = torch.empty((P,), dtype=torch.int32, device=dev)
+        totals = torch.empty((2,), dtype=torch.int32, device=dev)
+        p = _lib.LenRegParams(n_rows=P, n_utts=n_utts, dur=dptr(dur), utt_off=dptr(utt_off), frame_off=dptr(frame_off),
+                              utt_frame_off=dptr(utt_frame_off), order=dptr(order), totals=dptr(totals))
+        self._call("fcl_len_reg_scan", p)
+        return frame_off, utt_frame_off, order, totals
+
+    def frame_map(self, frame_off, utt_frame_off, n_rows, n_utts, n_frames, want_position=False):
+        dev = self.device
+        buf = torch.empty((4, max(n_frames, 1)), dtype=torch.int32, device=dev)
+        pos = torch.empty((max(n_frames, 1),), dtype=torch.float32, device=dev) if want_position else None
+        p = _lib.FrameMapParams(n_rows=n_rows, n_utts=n_utts, n_frames=n_frames, frame_off=dptr(frame_off),
+                                utt_frame_off=dptr(utt_frame_off), frame_row=dptr(buf[0]), frame_step=dptr(buf[1]),
+                                frame_seg_lo=dptr(buf[2]), frame_seg_hi=dptr(buf[3]), position=dptr(pos))
+        self._call("fcl_len_reg_frame_map", p)
+        return buf, pos
+
+    def decoder(self, hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p, dropout_seed,
+                tile_rows=None):
+        hp, w = self.hp, self.w
+        P, E, H, O = hn.shape[0], hp.eunits, hp.dunits, hp.odim
+        g0h = self.conv_gemm(hn, w["dec_g0h_w"], w["dec_g0h_b"], P, E, 4 * H, 1, ACT_NONE)
+        y0h = self.conv_gemm(hn, w["dec_y0h_w"], None, P, E, O, 1, ACT_NONE)
+        cstate = torch.empty((2, P, H), dtype=torch.float32, device=self.device)
+        before = torch.empty((max(n_frames, 1), O), dtype=torch.float32, device=self.device)
+        if tile_rows is None:
+            tile_rows = 32 if H <= 512 else 16
+        p = _lib.DecoderParams(n_rows=P, eunits=E, dunits=H, prenet_units=hp.prenet_units, odim=O, order=dptr(order),
+                               dur=dptr(dur), frame_off=dptr(frame_off), row_utt=dptr(row_utt), row_phone=dptr(row_phone),
+                               g0h=dptr(g0h), y0h=dptr(y0h), wp0=dptr(w["dec_wp0"]), bp0=dptr(w["dec_bp0"]),
+                               wp1=dptr(w["dec_wp1"]), bp1=dptr(w["dec_bp1"]), w0=dptr(w["dec_w0"]),
+                               wpos=dptr(w["dec_wpos"]), w1=dptr(w["dec_w1"]), b1=dptr(w["dec_b1"]), wf=dptr(w["dec_wf"]),
+                               cstate=dptr(cstate), before=dptr(before), zoneout=zoneout, dropout_p=dropout_p,
+                               dropout_seed=dropout_seed, tile_rows=tile_rows)
+        self._call("fcl_decoder_f32", p)
+        return before
+
+    def postnet(self, before, fseg, n_frames):
+        hp, w = self.hp, self.w
+        O, C = hp.odim, hp.postnet_chans
+        x = self.conv_gemm(before, w["post_conv0_w"], w["post_conv0_b"], n_frames, O, C, 5, ACT_TANH, seg=fseg)
+        for l in (1, 2, 3):
+            x = self.conv_gemm(x, w[f"post_conv{l}_w"], w[f"post_conv{l}_b"], n_frames, C, C, 5, ACT_TANH, seg=fseg)
+        return self.conv_gemm(x, w["post_conv4_w"], w["post_conv4_b"], n_frames, C, O, 5, ACT_NONE, seg=fseg,
+                              residual=before)
+
+    # ------------------------------------------------------------------ whole pass
+    def upload(self, plan: BatchPlan):
+        """One pinned staging buffer, one H2D copy. -> dict of device views + byte count."""
+        P, B = plan.n_rows, plan.n_utts
+        parts = [("ids", plan.ids.view(np.int32)), ("utt_off", plan.utt_off), ("row_utt", plan.row_utt),
+                 ("row_phone", plan.row_phone), ("seg_lo", plan.seg_lo), ("seg_hi", plan.seg_hi)]
+        if plan.dur is not None:
+            parts.append(("dur", np.minimum(plan.dur, _lib.MAX_DURATION).astype(np.int32)))
+        if plan.pitch is not None:
+            parts.append(("pitch", plan.pitch.view(np.int32)))
+            parts.append(("energy", plan.energy.view(np.int32)))
+        offs, total = {}, 0
+        for k, a in parts:
+            offs[k] = (total, a.shape[0])
+            total += (a.shape[0] + 3) // 4 * 4          # keep 16-byte alignment
+        stage = torch.empty((total,), dtype=torch.int32).pin_memory()
+        sn = stage.numpy()
+        for k, a in parts:
+            o, n = offs[k]
+            sn[o:o + n] = a
+        dev = stage.to(self.device, non_blocking=True)
+        v = {k: dev[o:o + n] for k, (o, n) in offs.items()}
+        v["ids"] = v["ids"].view(torch.int64)
+        for k in ("pitch", "energy"):
+            if k in v:
+                v[k] = v[k].view(torch.float32)
+        return v, total * 4
+
+    @torch.no_grad()
+    def run(self, plan: BatchPlan, zoneout: float, dropout_p: float, dropout_seed: int,
+            extras: bool = False, tile_rows=None) -> BatchResult:
+        hp = self.hp
+        B, P = plan.n_utts, plan.n_rows
+        d, h2d = self.upload(plan)
+        seg = (d["seg_lo"], d["seg_hi"])
+        ex = {"h2d_bytes": h2d}
+        h = self.encoder(d["ids"], d["utt_off"], seg, B)
+        need_pred_dur = plan.dur is None
+        dlog = None
+        if need_pred_dur or extras:
+            dlog, dur_pred = self.predictor("dur", h, seg, want_dur=True)
+        dur = dur_pred if need_pred_dur else d["dur"]
+        if plan.pitch is None:
+            pitch, _ = self.predictor("pitch", h, seg)
+            energy, _ = self.predictor("energy", h, seg)
+        else:
+            pitch, energy = d["pitch"], d["energy"]
+        hn = self.embed_add(h, pitch, energy, seg)
+        frame_off, utt_frame_off, order, totals = self.len_reg_scan(dur, d["utt_off"], B)
+        if need_pred_dur:
+            host = torch.cat([totals, utt_frame_off]).cpu().numpy()      # the one data-dependent D2H sync
+            F, ufo = int(host[0]), host[2:].astype(np.int64)
+            if int((dur == 0).sum()) != 0:
+                raise ValueError("predicted zero durations: outside the reference's working domain "
+                                 "(nets/modules/decoder_sa.py:575); pass dur=")
+        else:
+            if (plan.dur == 0).any():
+                raise ValueError("zero durations are outside the reference's working domain "
+                                 "(nets/modules/decoder_sa.py:575)")
+            per_utt = np.add.reduceat(np.minimum(plan.dur, _lib.MAX_DURATION).astype(np.int64), plan.utt_off[:-1].astype(np.int64))
+            ufo = np.concatenate([[0], np.cumsum(per_utt)])
+            F = int(ufo[-1])
+        before = self.decoder(hn, dur, frame_off, order, d["row_utt"], d["row_phone"], F, zoneout, dropout_p,
+                              dropout_seed, tile_rows)
+        fmap, pos = self.frame_map(frame_off, utt_frame_off, P, B, F, want_position=extras)
+        out = self.postnet(before, (fmap[2], fmap[3]), F)
+        if extras:
+            ex.update(h=h, dlog=dlog, dur_pred=dur_pred, pitch=pitch, energy=energy, hn=hn, before=before,
+                      frame_off=frame_off, order=order, frame_row=fmap[0], frame_step=fmap[1], position=pos,
+                      totals=totals, utt_frame_off_dev=utt_frame_off)
+        return BatchResult(out=out, utt_frame_off=ufo, perm=plan.perm, extras=ex)

@@ -1,0 +1,85 @@
+"""One-time weight repacking: reference `state_dict` -> kernel layouts.
+
+All transforms are exact re-arrangements except the eval-mode BatchNorm fold
+(scale into the conv weight, shift into a bias; encoder_sa.py:74, decoder_sa.py:213),
+done in fp32 on the host. Gate-interleaving puts i,f,g,o of one hidden unit in 4
+adjacent columns (torch.nn.LSTM/LSTMCell order is [i;f;g;o] blocks of H rows), so the
+LSTM cell update never leaves registers.
+"""
+from __future__ import annotations
+
+import torch
+
+from .hparams import HParams
+
+BN_EPS = 1e-5
+
+
+def _interleave_gates(w: torch.Tensor, hidden: int) -> torch.Tensor:
+    """(4H, K) rows [i;f;g;o] -> (K, 4H) with column u*4+g."""
+    k = w.shape[1]
+    return w.view(4, hidden, k).permute(2, 1, 0).reshape(k, 4 * hidden).contiguous()
+
+
+def _interleave_bias(b: torch.Tensor, hidden: int) -> torch.Tensor:
+    return b.view(4, hidden).t().reshape(4 * hidden).contiguous()
+
+
+def _fold_bn_conv(sd, conv_key: str, bn_prefix: str):
+    """Conv1d weight (Cout, Cin, k) + BatchNorm1d eval -> packed (k, Cin, Cout), bias (Cout)."""
+    w = sd[conv_key].float()
+    scale = sd[bn_prefix + ".weight"].float() / torch.sqrt(sd[bn_prefix + ".running_var"].float() + BN_EPS)
+    shift = sd[bn_prefix + ".bias"].float() - sd[bn_prefix + ".running_mean"].float() * scale
+    w = w * scale.view(-1, 1, 1)
+    return w.permute(2, 1, 0).contiguous(), shift.contiguous()
+
+
+def pack_fp32(sd, hp: HParams) -> dict:
+    """-> dict of contiguous fp32 CPU tensors in the layouts include/fcl_taco2.h documents."""
+    E, H, U, O = hp.eunits, hp.dunits, hp.prenet_units, hp.odim
+    hd = E // 2
+    f = lambda k: sd[k].detach().float().cpu()
+    out = {"embed": f("enc.embed.weight").contiguous()}
+    for l in range(3):
+        out[f"enc_conv{l}_w"], out[f"enc_conv{l}_b"] = _fold_bn_conv(
+            {k: f(k) for k in sd if k.startswith(f"enc.convs.{l}.")}, f"enc.convs.{l}.0.weight", f"enc.convs.{l}.1")
+    # BiLSTM: input projection for both directions as one (1, E, 8*hd) "conv", recurrent (2, hd, 4*hd)
+    wih = [_interleave_gates(f("enc.blstm.weight_ih_l0" + s), hd) for s in ("", "_reverse")]
+    bih = [_interleave_bias(f("enc.blstm.bias_ih_l0" + s) + f("enc.blstm.bias_hh_l0" + s), hd) for s in ("", "_reverse")]
+    out["blstm_wih"] = torch.cat(wih, dim=1).unsqueeze(0).contiguous()
+    out["blstm_b"] = torch.cat(bih).contiguous()
+    out["blstm_whh"] = torch.stack([_interleave_gates(f("enc.blstm.weight_hh_l0" + s), hd) for s in ("", "_reverse")]).contiguous()
+    for name, short in (("duration_predictor", "dur"), ("pitch_predictor", "pitch"), ("energy_predictor", "energy")):
+        for l in range(2):
+            out[f"{short}_conv{l}_w"] = f(f"{name}.conv.{l}.0.weight").permute(2, 1, 0).contiguous()
+            out[f"{short}_conv{l}_b"] = f(f"{name}.conv.{l}.0.bias").contiguous()
+            out[f"{short}_ln{l}_g"] = f(f"{name}.conv.{l}.2.weight").contiguous()
+            out[f"{short}_ln{l}_b"] = f(f"{name}.conv.{l}.2.bias").contiguous()
+        out[f"{short}_head_w"] = f(f"{name}.linear.weight").reshape(-1).contiguous()
+        out[f"{short}_head_b"] = f(f"{name}.linear.bias").reshape(-1).contiguous()
+    for name, short in (("pitch_embed", "pemb"), ("energy_embed", "eemb")):
+        out[f"{short}_w"] = f(f"{name}.0.weight").reshape(E, -1).contiguous()
+        out[f"{short}_b"] = f(f"{name}.0.bias").contiguous()
+    # decoder
+    wih0, whh0 = f("dec.lstm.0.cell.weight_ih"), f("dec.lstm.0.cell.weight_hh")
+    assert wih0.shape[1] == E + U + 1
+    out["dec_g0h_w"] = _interleave_gates(wih0[:, :E].contiguous(), H).unsqueeze(0).contiguous()         # (1, E, 4H)
+    out["dec_g0h_b"] = _interleave_bias(f("dec.lstm.0.cell.bias_ih") + f("dec.lstm.0.cell.bias_hh"), H)
+    out["dec_w0"] = torch.cat([_interleave_gates(wih0[:, E:E + U].contiguous(), H), _interleave_gates(whh0, H)], dim=0).contiguous()
+    out["dec_wpos"] = _interleave_bias(wih0[:, E + U].contiguous(), H)
+    out["dec_w1"] = torch.cat([_interleave_gates(f("dec.lstm.1.cell.weight_ih"), H),
+                               _interleave_gates(f("dec.lstm.1.cell.weight_hh"), H)], dim=0).contiguous()
+    out["dec_b1"] = _interleave_bias(f("dec.lstm.1.cell.bias_ih") + f("dec.lstm.1.cell.bias_hh"), H)
+    out["dec_wp0"] = f("dec.prenet.prenet.0.0.weight").t().contiguous()
+    out["dec_bp0"] = f("dec.prenet.prenet.0.0.bias").contiguous()
+    out["dec_wp1"] = f("dec.prenet.prenet.1.0.weight").t().contiguous()
+    out["dec_bp1"] = f("dec.prenet.prenet.1.0.bias").contiguous()
+    wfeat = f("dec.feat_out.weight")
+    assert wfeat.shape == (O, H + E)
+    out["dec_wf"] = wfeat[:, :H].t().contiguous()                                                        # (H, O)
+    out["dec_y0h_w"] = wfeat[:, H:].t().contiguous().unsqueeze(0).contiguous()                           # (1, E, O)
+    for l in range(5):
+        out[f"post_conv{l}_w"], out[f"post_conv{l}_b"] = _fold_bn_conv(
+            {k: f(k) for k in sd if k.startswith(f"dec.postnet.postnet.{l}.")},
+            f"dec.postnet.postnet.{l}.0.weight", f"dec.postnet.postnet.{l}.1")
+    return out

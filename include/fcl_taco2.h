@@ -1,0 +1,200 @@
+/*
+ * fcl_taco2.h -- C ABI of the B200 (sm_100a) FCL-taco2 inference path.
+ *
+ * The reference (Wendison/FCL-taco2) is pure Python on top of torch ops; it has
+ * no FFI of its own. Each entry point below replaces the torch ops of one row
+ * of SURVEY.md section 8(a); the reference lines it stands for are cited on each
+ * declaration. INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", POD structs, raw DEVICE pointers, explicit sizes; no torch types.
+ *   - No allocation inside: the caller owns every buffer, including scratch.
+ *   - Work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises the host.
+ *   - Return 0 on success, a negative FCL_E* code otherwise; fcl_last_error()
+ *     returns a thread-local message. Nothing throws.
+ *   - "rows" are phonemes (ragged-packed over the utterances of a batch, an
+ *     utterance = a contiguous row range) or mel frames (same, per utterance).
+ *     Activations are row-major (rows, channels) fp32.
+ *   - There is no CPU fallback: with no CUDA device every launch returns FCL_ECUDA.
+ */
+#ifndef FCL_TACO2_H_
+#define FCL_TACO2_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCL_ABI_VERSION 3
+
+enum {
+  FCL_OK = 0,
+  FCL_EINVAL = -1,   /* bad argument (null pointer, unsupported size)            */
+  FCL_ECUDA = -2,    /* CUDA runtime error (message has cudaGetErrorString)      */
+  FCL_EUNSUPPORTED = -3
+};
+
+enum { FCL_ACT_NONE = 0, FCL_ACT_RELU = 1, FCL_ACT_TANH = 2 };
+
+int fcl_abi_version(void);
+const char* fcl_last_error(void);
+/* Number of SMs of the current device (grid sizing on the host side); <0 on error. */
+int fcl_sm_count(void);
+/* sizeof() of parameter struct number `which` (declaration order in this header, 0-based); a binding
+ * in another language checks its own layout against it. -1 for an unknown index. */
+int fcl_struct_size(int which);
+
+/* ---------------------------------------------------------------- K0: length regulator
+ * Replaces the Python loops of nets/teacher_training/e2e_tts_tacotron2_sa.py:665-671
+ * (position table) and nets/modules/decoder_sa.py:619-630 (ragged gather order):
+ * durations -> exclusive scan (frame offset of every phoneme row), per-utterance
+ * frame offsets, the frame -> (row, step) index map, and a duration-descending
+ * row order used to form decoder tiles. Integer work, bit-exact.
+ */
+typedef struct {
+  int32_t n_rows;            /* P: phoneme rows in the batch                               */
+  int32_t n_utts;            /* B                                                          */
+  const int32_t* dur;        /* (P)  durations, >= 0 (0 rows produce no frames)            */
+  const int32_t* utt_off;    /* (B+1) row offset of each utterance                         */
+  int32_t* frame_off;        /* out (P+1) exclusive scan of dur                            */
+  int32_t* utt_frame_off;    /* out (B+1) frame offset of each utterance                   */
+  int32_t* order;            /* out (P)  rows sorted by duration, descending               */
+  int32_t* totals;           /* out (2)  [0]=F total frames, [1]=max duration              */
+} FclLenRegParams;
+#define FCL_MAX_DURATION 1023      /* durations are clamped to this (reference data cap is 50) */
+int fcl_len_reg_scan(const FclLenRegParams* p, void* stream);
+
+typedef struct {
+  int32_t n_rows, n_utts, n_frames;
+  const int32_t* frame_off;      /* (P+1) */
+  const int32_t* utt_frame_off;  /* (B+1) */
+  int32_t* frame_row;            /* out (F) row of each frame                                */
+  int32_t* frame_step;           /* out (F) step m of each frame within its row              */
+  int32_t* frame_seg_lo;         /* out (F) first frame of the frame's utterance             */
+  int32_t* frame_seg_hi;         /* out (F) one past the last frame of the frame's utterance */
+  float* position;               /* optional out (F): float(m)/float(d) (IEEE division)      */
+} FclFrameMapParams;
+int fcl_len_reg_frame_map(const FclFrameMapParams* p, void* stream);
+
+/* ---------------------------------------------------------------- ragged conv1d / linear as GEMM
+ * out[r, n] = act( sum_{t<taps} sum_{c<cin} A[r + t - taps/2, c] * W[t][c][n] + bias[n] ) (+ residual[r, n])
+ * with A rows outside [seg_lo[r], seg_hi[r]) read as zero (zero halo per utterance,
+ * never "pad and convolve": SURVEY.md 3.4). Replaces torch.nn.Conv1d (+ folded
+ * eval-mode BatchNorm1d) + ReLU/Tanh of nets/modules/encoder_sa.py:135-140,
+ * nets/modules/decoder_sa.py:274-286,632, the Conv1d of variance_predictor.py:86-87,
+ * and torch.nn.Linear where taps == 1. With `gather` != NULL, A row r is
+ * table row gather[r] (torch.nn.Embedding, encoder_sa.py:134).
+ */
+typedef struct {
+  int32_t rows, cin, cout, taps;
+  const float* a;            /* (rows, lda) or the embedding table when gather != NULL     */
+  int32_t lda;
+  const int64_t* gather;     /* optional (rows) int64 ids                                  */
+  const int32_t* seg_lo;     /* (rows) or NULL when taps == 1                              */
+  const int32_t* seg_hi;
+  const float* w;            /* packed (taps, cin, cout) fp32                              */
+  const float* bias;         /* optional (cout)                                            */
+  const float* residual;     /* optional (rows, ldr)                                       */
+  int32_t ldr;
+  float* out;                /* (rows, ldo)                                                */
+  int32_t ldo;
+  int32_t act;               /* FCL_ACT_*                                                  */
+} FclConvGemmParams;
+int fcl_conv_gemm_f32(const FclConvGemmParams* p, void* stream);
+
+/* ---------------------------------------------------------------- LayerNorm (+ optional head)
+ * y = LayerNorm_C(x) * gamma + beta, eps 1e-12 (espnet LayerNorm, variance_predictor.py:62).
+ * If head_w != NULL: head[r] = dot(y[r], head_w) + head_b (Linear(C,1), variance_predictor.py:90)
+ * and, if dur_out != NULL, dur_out[r] = clamp(round_half_even(exp(head[r]) - 1), 0, FCL_MAX_DURATION)
+ * (espnet DurationPredictor.inference). `y` may be NULL when only the head is wanted.
+ */
+typedef struct {
+  int32_t rows, chans;
+  const float* x;            /* (rows, chans) */
+  const float* gamma;
+  const float* beta;
+  float* y;                  /* optional (rows, chans) */
+  const float* head_w;       /* optional (chans) */
+  float head_b;
+  float* head_out;           /* optional (rows) */
+  int32_t* dur_out;          /* optional (rows) */
+} FclLayerNormParams;
+int fcl_layernorm_f32(const FclLayerNormParams* p, void* stream);
+
+/* ---------------------------------------------------------------- pitch/energy embed + add
+ * hn[r, e] = h[r, e] + sum_j wp[e][j]*pitch[r+j-4] + bp[e] + sum_j we[e][j]*energy[r+j-4] + be[e]
+ * (Conv1d(1,E,k=9,pad=4) over the phoneme axis of each utterance,
+ * e2e_tts_tacotron2_sa.py:435-443,657-658; add: decoder_sa.py:570-571).
+ */
+typedef struct {
+  int32_t rows, chans, taps;
+  const float* h;            /* (rows, chans) */
+  const float* pitch;        /* (rows) */
+  const float* energy;       /* (rows) */
+  const int32_t* seg_lo;
+  const int32_t* seg_hi;
+  const float* wp;           /* (chans, taps) */
+  const float* bp;
+  const float* we;
+  const float* be;
+  float* hn;                 /* out (rows, chans) */
+} FclEmbedAddParams;
+int fcl_embed_add_f32(const FclEmbedAddParams* p, void* stream);
+
+/* ---------------------------------------------------------------- encoder BiLSTM recurrence
+ * torch.nn.LSTM(E, E/2, 1, bidirectional) of nets/modules/encoder_sa.py:96-100,143-146
+ * on every utterance of the batch independently. The input projection (x W_ih^T + b_ih + b_hh,
+ * both directions) is done beforehand with fcl_conv_gemm_f32 into `gx`.
+ */
+typedef struct {
+  int32_t n_utts, hidden;    /* hidden = E/2 per direction                                 */
+  const int32_t* utt_off;    /* (B+1)                                                      */
+  const float* gx;           /* (P, 2, hidden*4) gate-interleaved: col = dir*4H + unit*4 + gate(i,f,g,o) */
+  const float* whh;          /* (2, hidden, hidden*4) : [dir][k][unit*4+gate] = W_hh[gate*H+unit][k]      */
+  float* out;                /* (P, 2*hidden): [fwd | bwd]                                 */
+  int32_t group;             /* utterances per CTA: 1 or 8                                 */
+} FclBiLstmParams;
+int fcl_bilstm_f32(const FclBiLstmParams* p, void* stream);
+
+/* ---------------------------------------------------------------- K4: persistent decoder
+ * The step loop of nets/modules/decoder_sa.py:577-617 (Prenet :146-158 with its always-on
+ * dropout, ZoneOutCell :63-96 around torch.nn.LSTMCell, feat_out :398) fused with the ragged
+ * gather of :619-630: every CTA owns a tile of duration-sorted rows, keeps z/c state on chip
+ * for all steps and stores frame (row, m) straight to before[frame_off[row] + m] for m < d.
+ * The step-invariant terms are hoisted (gemm beforehand):
+ *   g0h = hn W_ih0[:, :E]^T + b_ih0 + b_hh0   (P, 4H) gate-interleaved
+ *   y0h = hn W_feat[:, H:]^T                  (P, O)
+ */
+typedef struct {
+  int32_t n_rows, eunits, dunits, prenet_units, odim;
+  const int32_t* order;      /* (P) duration-descending row order (fcl_len_reg_scan)      */
+  const int32_t* dur;        /* (P)                                                        */
+  const int32_t* frame_off;  /* (P+1)                                                      */
+  const int32_t* row_utt;    /* (P) dropout key: utterance index of the row               */
+  const int32_t* row_phone;  /* (P) dropout key: phoneme index within the utterance       */
+  const float* g0h;          /* (P, 4H)                                                    */
+  const float* y0h;          /* (P, O)                                                     */
+  const float* wp0;          /* (O, U)   = prenet.0 weight^T                               */
+  const float* bp0;          /* (U)                                                        */
+  const float* wp1;          /* (U, U)   = prenet.1 weight^T                               */
+  const float* bp1;
+  const float* w0;           /* (U + H, 4H) rows [prenet part of W_ih0 ; W_hh0]^T, gate-interleaved cols */
+  const float* wpos;         /* (4H)  position column of W_ih0, gate-interleaved           */
+  const float* w1;           /* (2H, 4H) rows [W_ih1 ; W_hh1]^T, gate-interleaved cols     */
+  const float* b1;           /* (4H)  b_ih1 + b_hh1, gate-interleaved                      */
+  const float* wf;           /* (H, O) = W_feat[:, :H]^T                                   */
+  float* cstate;             /* scratch (2, P, H) cell states                              */
+  float* before;             /* out (F, O)                                                 */
+  float zoneout;
+  float dropout_p;           /* 0 => prenet dropout off                                    */
+  uint64_t dropout_seed;
+  int32_t tile_rows;         /* 16 or 32                                                   */
+} FclDecoderParams;
+int fcl_decoder_f32(const FclDecoderParams* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* FCL_TACO2_H_ */

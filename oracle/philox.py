@@ -8,7 +8,7 @@ implementations. The B200 path defines the keep decision as a pure function
         key     = (seed & 0xffffffff, seed >> 32),
         counter = (unit >> 2, step | layer << 24, phoneme, utt))[unit & 3] >= thresh(p)
 
-with thresh(p) = min(round(p * 2**32), 2**32 - 1). This file restates that
+with thresh(p) = min(floor(float32(p) * 2**32 + 0.5), 2**32 - 1). This file restates that
 definition on the CPU (the CUDA copy is fcl_taco2_b200/csrc/philox.cuh); the
 oracle injects it into the reference through oracle.ref_loader.prenet_dropout.
 Philox4x32-10 is Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"
@@ -42,7 +42,8 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def threshold(p: float) -> int:
-    return min(int(round(float(p) * 4294967296.0)), 4294967295)
+    """p is taken as float32 (what the CUDA side receives); float32(p) * 2**32 is an integer for p >= 2**-9."""
+    return min(int(float(np.float32(p)) * 4294967296.0 + 0.5), 4294967295)
 
 
 def keep_mask(seed: int, utt, phoneme, step: int, layer: int, n_units: int, p: float) -> np.ndarray:
