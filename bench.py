@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- mel frames/s of the FCL-taco2 inference hot path on B200 (see DESIGN.md "Measurement").
+
+  python bench.py --gpus 1 --steps 10 --warmup 3                       # our arm
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...                                 # the reference's CPU path (oracle port)
+
+A "step" = one pass of the whole hot path (encoder -> predictors -> length regulator -> decoder
+-> postnet) over one synthetic LJSpeech-shaped batch. `value` = frames of all ranks / device time
+(inputs resident in HBM); `e2e` = the same through model.inference_batch() with host buffers
+(H2D of the inputs and D2H of the mels inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from fcl_taco2_b200 import synth, hparams            # noqa: E402
+
+# algorithmic work per unit (SURVEY.md 8(d) / BASELINE.md 3), MAC counts of the reference formulation
+MACS = {
+    "S": dict(decoder_row_step=1_438_720, postnet_frame=348_160, front_phoneme=3_593_856),
+    "T": dict(decoder_row_step=15_941_632, postnet_frame=4_341_760, front_phoneme=8_611_968),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sust=j["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(args, rank):
+    """LJSpeech-shaped synthetic batch for this rank; different seed per rank (weak scaling)."""
+    xs, ds = synth.synth_batch(args.batch, seed=args.seed + 1000 * rank, stress=args.stress,
+                               fixed_len=500 if args.stress else None)
+    return xs, ds
+
+
+def cpu_port_time(kind, xs, ds, budget_s, seed):
+    """Time the oracle port (the reference's algorithm on torch CPU, per-utterance loop like
+    tts.py:655-674) on a bounded sample. -> (frames/s, n_utts, frames, seconds, threads)"""
+    from oracle import restate          # CPU baseline leg: the only place bench.py touches oracle/
+    torch.set_num_threads(os.cpu_count())
+    sd = synth.random_state_dict(hparams.preset(kind), seed)
+    drop = restate.Dropout(0.5, 1, native=True)       # torch's F.dropout, as the reference runs it
+    with torch.no_grad():
+        restate.inference(sd, torch.from_numpy(xs[0]), dur=ds[0], dropout=drop, fast_lstm=True)     # warm-up
+        t0 = time.perf_counter()
+        frames = n = 0
+        for x, d in zip(xs, ds):
+            out = restate.inference(sd, torch.from_numpy(x), dur=d, dropout=drop, utt_index=n, fast_lstm=True)
+            frames += out.shape[0]
+            n += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        dt = time.perf_counter() - t0
+    return frames / dt, n, frames, dt, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    xs, ds = workload(args, 0)
+    vals, last = [], None
+    for it in range(args.warmup + args.steps):
+        last = cpu_port_time(args.model, xs, ds, budget_s=max(2.0, 60.0 / max(1, args.steps + args.warmup)), seed=args.seed)
+        if it >= args.warmup:
+            vals.append(last)
+    fps = sum(v[2] for v in vals) / sum(v[3] for v in vals)
+    sample = f"first {vals[-1][1]} utterances ({vals[-1][2]} frames) of the batch-{args.batch} workload per step, per-utterance loop"
+    line = {
+        "metric": "mel frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(v[3] for v in vals) / len(vals), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": config_dict(args, world),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": vals[-1][4], "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference is Python and cannot travel to the GPU box: this is oracle/restate.py, the op-for-op "
+                "torch-CPU restatement validated against the reference in the build container",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, world):
+    return {"workload": f"FCL-taco2-{args.model} batched inference, batch {args.batch} synthetic LJSpeech-shaped "
+                        f"utterances per GPU" + (" (500-phoneme stress)" if args.stress else ""),
+            "model_size": args.model, "per_gpu_batch": args.batch, "global_batch": args.batch * world,
+            "precision": args.precision, "prenet_dropout": 0.5, "forced_durations": True,
+            "parallelism": f"utterance-sharded x{world}, no hot-path collective, final mel gather to rank 0",
+            "l2": "flushed between timed steps (256 MiB write, outside the per-step events)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="S", choices=["S", "T"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--stress", action="store_true")
+    ap.add_argument("--latency-utts", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from fcl_taco2_b200 import model as M, plan as planmod, dist as fdist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    m = M.from_preset(args.model, seed=args.seed, device=dev, precision=args.precision)
+    m.set_prenet_dropout(rate=0.5, seed=1)
+    eng = m.engine()
+    xs, ds = workload(args, rank)
+    pl = planmod.make_plan(xs, ds)
+    n_frames = int(sum(int(d.sum()) for d in ds))
+    n_rows = pl.n_rows
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    dinp, h2d_bytes = eng.upload(pl)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_step(timed):
+        flush.fill_(rank + 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.stage_events = [] if timed else None
+        e0.record()
+        res = eng.run_uploaded(pl, dinp, m.hp.zoneout_rate, 0.5, 1)
+        gathered = fdist.gather_mels(res.out) if world > 1 else None
+        e1.record()
+        return e0, e1, res, eng.stage_events, gathered
+
+    for _ in range(args.warmup):
+        one_step(False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    evs = [one_step(True) for _ in range(args.steps)]
+    barrier()
+    launches = eng.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [e0.elapsed_time(e1) for e0, e1, *_ in evs]
+    total_ms = float(sum(step_ms))
+    stage_ms = {}
+    for _, _, _, se, _ in evs:
+        for name, a, b in se:
+            stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b)
+    eng.stage_events = None
+
+    # ---- e2e through the public API: host ids/durations in, host mels out
+    host_out = torch.empty((n_frames, m.odim), dtype=torch.float32).pin_memory()
+    def e2e_step():
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = m.inference_batch(xs, durs=ds, return_result=True)
+        host_out.copy_(res.out, non_blocking=True)
+        e1.record()
+        return e0, e1
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_evs = [e2e_step() for _ in range(args.steps)]
+    barrier()
+    e2e_ms = float(sum(a.elapsed_time(b) for a, b in e2e_evs))
+
+    # ---- reduce over ranks: max time, sum frames
+    t = torch.tensor([total_ms, e2e_ms, float(n_frames), float(n_rows), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, e2e_ms = float(tmax[0]), float(tmax[1])
+        all_frames, all_rows, all_launches = float(tsum[2]), float(tsum[3]), int(tsum[4])
+    else:
+        all_frames, all_rows, all_launches = float(n_frames), float(n_rows), launches
+
+    if rank == 0:
+        pk = peaks()
+        macs = MACS[args.model]
+        dec_ms = stage_ms.get("decoder_loop", 0.0) / args.steps
+        dec_flops = 2.0 * macs["decoder_row_step"] * n_frames
+        achieved = dec_flops / (dec_ms * 1e-3) / 1e12 if dec_ms > 0 else 0.0
+        value = all_frames * args.steps / (total_ms * 1e-3)
+        line = {
+            "metric": "mel frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": config_dict(args, world),
+            "frames_per_step": all_frames, "phoneme_rows_per_step": all_rows,
+            "clocks": clocks,
+            "e2e": {"value": all_frames * args.steps / (e2e_ms * 1e-3), "unit": "frames/s",
+                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(n_frames * m.odim * 4),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": all_launches,
+            "roofline": {"kernel": "decoder step loop (fcl_decoder_*), rank 0", "bound": "tensor", "achieved": achieved,
+                         "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"], "traffic": None,
+                         "peak_source": pk["src"] + " bf16_tflops_sustained", "ms_per_launch": dec_ms,
+                         "algorithmic_flops_per_launch": dec_flops,
+                         "note": "algorithmic FLOPs = 2 x MAC per useful row-step (reference formulation, nothing hoisted) x frames"},
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+        }
+        if not args.no_extra:
+            line["p50_utt_latency_ms"] = latency_p50(m, args, dev)
+        if not args.no_cpu_baseline:
+            fps, n, fr, dt, thr = cpu_port_time(args.model, xs, ds, budget_s=15.0, seed=args.seed)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": thr, "kind": "port",
+                                    "sample": f"first {n} utterances ({fr} frames) of the same workload, per-utterance "
+                                              f"loop of oracle/restate.py (torch CPU fp32), {dt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def latency_p50(m, args, dev):
+    """p50 single-utterance latency (batch = 1), device-timed through the public API with host input."""
+    xs, ds = synth.synth_batch(args.latency_utts, seed=args.seed + 77)
+    lat = []
+    for i, (x, d) in enumerate(zip(xs, ds)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        m.inference(torch.from_numpy(x), None, dur=d)
+        e1.record()
+        e1.synchronize()
+        if i >= 5:
+            lat.append(e0.elapsed_time(e1))
+    return float(np.median(lat))
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,7 @@ class Engine:
         self.w = {k: v.to(self.device) for k, v in packed.items()}
         self.head_b = {s: float(packed[f"{s}_head_b"][0]) for s in ("dur", "pitch", "energy")}
         self.launches = 0
+        self.stage_events = None      # when a list: (stage, start_event, stop_event) appended per stage (bench.py)
 
     # ------------------------------------------------------------------ launch helpers
     def _stream(self):
@@ -139,8 +140,9 @@ class Engine:
                 tile_rows=None):
         hp, w = self.hp, self.w
         P, E, H, O = hn.shape[0], hp.eunits, hp.dunits, hp.odim
-        g0h = self.conv_gemm(hn, w["dec_g0h_w"], w["dec_g0h_b"], P, E, 4 * H, 1, ACT_NONE)
-        y0h = self.conv_gemm(hn, w["dec_y0h_w"], None, P, E, O, 1, ACT_NONE)
+        with self.stage("decoder_hoist"):
+            g0h = self.conv_gemm(hn, w["dec_g0h_w"], w["dec_g0h_b"], P, E, 4 * H, 1, ACT_NONE)
+            y0h = self.conv_gemm(hn, w["dec_y0h_w"], None, P, E, O, 1, ACT_NONE)
         cstate = torch.empty((2, P, H), dtype=torch.float32, device=self.device)
         before = torch.empty((max(n_frames, 1), O), dtype=torch.float32, device=self.device)
         if tile_rows is None:
@@ -152,7 +154,8 @@ class Engine:
                                wpos=dptr(w["dec_wpos"]), w1=dptr(w["dec_w1"]), b1=dptr(w["dec_b1"]), wf=dptr(w["dec_wf"]),
                                cstate=dptr(cstate), before=dptr(before), zoneout=zoneout, dropout_p=dropout_p,
                                dropout_seed=dropout_seed, tile_rows=tile_rows)
-        self._call("fcl_decoder_f32", p)
+        with self.stage("decoder_loop"):
+            self._call("fcl_decoder_f32", p)
         return before
 
     def postnet(self, before, fseg, n_frames):
@@ -192,27 +195,54 @@ class Engine:
                 v[k] = v[k].view(torch.float32)
         return v, total * 4
 
+    class _Stage:
+        def __init__(self, eng, name):
+            self.eng, self.name = eng, name
+
+        def __enter__(self):
+            if self.eng.stage_events is not None:
+                self.t0 = torch.cuda.Event(enable_timing=True)
+                self.t0.record(torch.cuda.current_stream(self.eng.device))
+
+        def __exit__(self, *a):
+            if self.eng.stage_events is not None:
+                t1 = torch.cuda.Event(enable_timing=True)
+                t1.record(torch.cuda.current_stream(self.eng.device))
+                self.eng.stage_events.append((self.name, self.t0, t1))
+
+    def stage(self, name):
+        return Engine._Stage(self, name)
+
     @torch.no_grad()
     def run(self, plan: BatchPlan, zoneout: float, dropout_p: float, dropout_seed: int,
             extras: bool = False, tile_rows=None) -> BatchResult:
+        d, h2d = self.upload(plan)
+        return self.run_uploaded(plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d)
+
+    @torch.no_grad()
+    def run_uploaded(self, plan: BatchPlan, d: dict, zoneout: float, dropout_p: float, dropout_seed: int,
+                     extras: bool = False, tile_rows=None, h2d: int = 0) -> BatchResult:
+        """The pass proper, inputs already resident on the device (`d` from `upload`)."""
         hp = self.hp
         B, P = plan.n_utts, plan.n_rows
-        d, h2d = self.upload(plan)
         seg = (d["seg_lo"], d["seg_hi"])
         ex = {"h2d_bytes": h2d}
-        h = self.encoder(d["ids"], d["utt_off"], seg, B)
+        with self.stage("encoder"):
+            h = self.encoder(d["ids"], d["utt_off"], seg, B)
         need_pred_dur = plan.dur is None
-        dlog = None
-        if need_pred_dur or extras:
-            dlog, dur_pred = self.predictor("dur", h, seg, want_dur=True)
-        dur = dur_pred if need_pred_dur else d["dur"]
-        if plan.pitch is None:
-            pitch, _ = self.predictor("pitch", h, seg)
-            energy, _ = self.predictor("energy", h, seg)
-        else:
-            pitch, energy = d["pitch"], d["energy"]
-        hn = self.embed_add(h, pitch, energy, seg)
-        frame_off, utt_frame_off, order, totals = self.len_reg_scan(dur, d["utt_off"], B)
+        dlog = dur_pred = None
+        with self.stage("predictors"):
+            if need_pred_dur or extras:
+                dlog, dur_pred = self.predictor("dur", h, seg, want_dur=True)
+            dur = dur_pred if need_pred_dur else d["dur"]
+            if plan.pitch is None:
+                pitch, _ = self.predictor("pitch", h, seg)
+                energy, _ = self.predictor("energy", h, seg)
+            else:
+                pitch, energy = d["pitch"], d["energy"]
+            hn = self.embed_add(h, pitch, energy, seg)
+        with self.stage("len_reg"):
+            frame_off, utt_frame_off, order, totals = self.len_reg_scan(dur, d["utt_off"], B)
         if need_pred_dur:
             host = torch.cat([totals, utt_frame_off]).cpu().numpy()      # the one data-dependent D2H sync
             F, ufo = int(host[0]), host[2:].astype(np.int64)
@@ -228,8 +258,10 @@ class Engine:
             F = int(ufo[-1])
         before = self.decoder(hn, dur, frame_off, order, d["row_utt"], d["row_phone"], F, zoneout, dropout_p,
                               dropout_seed, tile_rows)
-        fmap, pos = self.frame_map(frame_off, utt_frame_off, P, B, F, want_position=extras)
-        out = self.postnet(before, (fmap[2], fmap[3]), F)
+        with self.stage("frame_map"):
+            fmap, pos = self.frame_map(frame_off, utt_frame_off, P, B, F, want_position=extras)
+        with self.stage("postnet"):
+            out = self.postnet(before, (fmap[2], fmap[3]), F)
         if extras:
             ex.update(h=h, dlog=dlog, dur_pred=dur_pred, pitch=pitch, energy=energy, hn=hn, before=before,
                       frame_off=frame_off, order=order, frame_row=fmap[0], frame_step=fmap[1], position=pos,
