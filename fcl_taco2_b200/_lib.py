@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -32,6 +32,12 @@ class ConvGemmParams(C.Structure):
     _fields_ = [("rows", i32), ("cin", i32), ("cout", i32), ("taps", i32), ("a", ptr), ("lda", i32),
                 ("gather", ptr), ("seg_lo", ptr), ("seg_hi", ptr), ("w", ptr), ("bias", ptr), ("residual", ptr),
                 ("ldr", i32), ("out", ptr), ("ldo", i32), ("act", i32)]
+
+
+class ConvGemmBf16Params(C.Structure):
+    _fields_ = [("rows", i32), ("cin", i32), ("cout", i32), ("taps", i32), ("a", ptr), ("lda", i32),
+                ("gather", ptr), ("seg_lo", ptr), ("seg_hi", ptr), ("w_packed", ptr), ("ntile", i32), ("kstage", i32),
+                ("bias", ptr), ("residual", ptr), ("ldr", i32), ("out", ptr), ("ldo", i32), ("act", i32)]
 
 
 class LayerNormParams(C.Structure):
@@ -58,7 +64,7 @@ class DecoderParams(C.Structure):
 
 
 STRUCTS = [LenRegParams, FrameMapParams, ConvGemmParams, LayerNormParams, EmbedAddParams, BiLstmParams,
-           DecoderParams]
+           DecoderParams, ConvGemmBf16Params]
 
 ENTRY_POINTS = {
     "fcl_len_reg_scan": LenRegParams,
@@ -68,6 +74,7 @@ ENTRY_POINTS = {
     "fcl_embed_add_f32": EmbedAddParams,
     "fcl_bilstm_f32": BiLstmParams,
     "fcl_decoder_f32": DecoderParams,
+    "fcl_conv_gemm_bf16": ConvGemmBf16Params,
 }
 PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_last_error", "fcl_sm_count", "fcl_struct_size"]
 

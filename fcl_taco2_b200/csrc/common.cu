@@ -43,6 +43,7 @@ extern "C" int fcl_struct_size(int which) {
     case 4: return (int)sizeof(FclEmbedAddParams);
     case 5: return (int)sizeof(FclBiLstmParams);
     case 6: return (int)sizeof(FclDecoderParams);
+    case 7: return (int)sizeof(FclConvGemmBf16Params);
     default: return -1;
   }
 }

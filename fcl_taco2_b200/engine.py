@@ -40,7 +40,7 @@ class BatchResult:
 class Engine:
     def __init__(self, hp: HParams, packed: dict, device, precision: str = "fp32"):
         hp.validate()
-        if precision not in ("fp32",):
+        if precision not in ("fp32", "bf16"):
             raise ValueError(f"unknown precision {precision!r}")
         self.hp, self.precision = hp, precision
         self.device = torch.device(device)
@@ -48,6 +48,10 @@ class Engine:
             raise _lib.FclError("the B200 path runs on CUDA devices only (no CPU fallback)")
         _lib.load()
         self.w = {k: v.to(self.device) for k, v in packed.items()}
+        self.wb = {}
+        if precision == "bf16":
+            from . import pack as _pack
+            self.wb = {k: (t.to(self.device), nt, ks) for k, (t, nt, ks) in _pack.pack_bf16(packed).items()}
         self.head_b = {s: float(packed[f"{s}_head_b"][0]) for s in ("dur", "pitch", "energy")}
         self.launches = 0
         self.stage_events = None      # when a list: (stage, start_event, stop_event) appended per stage (bench.py)
@@ -61,9 +65,18 @@ class Engine:
         self.launches += 1
 
     def conv_gemm(self, a, w, bias, rows, cin, cout, taps, act, seg=None, gather=None, residual=None, out=None,
-                  lda=None):
+                  lda=None, key=None):
         if out is None:
             out = torch.empty((rows, cout), dtype=torch.float32, device=self.device)
+        if key is not None and key in self.wb:
+            wp, ntile, kstage = self.wb[key]
+            p = _lib.ConvGemmBf16Params(rows=rows, cin=cin, cout=cout, taps=taps, a=dptr(a), lda=lda or cin,
+                                        gather=dptr(gather), seg_lo=dptr(seg[0]) if seg else None,
+                                        seg_hi=dptr(seg[1]) if seg else None, w_packed=dptr(wp), ntile=ntile,
+                                        kstage=kstage, bias=dptr(bias), residual=dptr(residual), ldr=cout,
+                                        out=dptr(out), ldo=cout, act=act)
+            self._call("fcl_conv_gemm_bf16", p)
+            return out
         p = _lib.ConvGemmParams(rows=rows, cin=cin, cout=cout, taps=taps, a=dptr(a), lda=lda or cin,
                                 gather=dptr(gather), seg_lo=dptr(seg[0]) if seg else None,
                                 seg_hi=dptr(seg[1]) if seg else None, w=dptr(w), bias=dptr(bias),
@@ -82,10 +95,12 @@ class Engine:
         hp, w = self.hp, self.w
         P, E = ids.shape[0], hp.eunits
         x = self.conv_gemm(w["embed"], w["enc_conv0_w"], w["enc_conv0_b"], P, hp.embed_dim, hp.econv_chans, 5,
-                           ACT_RELU, seg=seg, gather=ids)
-        x = self.conv_gemm(x, w["enc_conv1_w"], w["enc_conv1_b"], P, hp.econv_chans, hp.econv_chans, 5, ACT_RELU, seg=seg)
-        x = self.conv_gemm(x, w["enc_conv2_w"], w["enc_conv2_b"], P, hp.econv_chans, hp.econv_chans, 5, ACT_RELU, seg=seg)
-        gx = self.conv_gemm(x, w["blstm_wih"], w["blstm_b"], P, hp.econv_chans, 4 * E, 1, ACT_NONE)
+                           ACT_RELU, seg=seg, gather=ids, key="enc_conv0")
+        x = self.conv_gemm(x, w["enc_conv1_w"], w["enc_conv1_b"], P, hp.econv_chans, hp.econv_chans, 5, ACT_RELU, seg=seg,
+                           key="enc_conv1")
+        x = self.conv_gemm(x, w["enc_conv2_w"], w["enc_conv2_b"], P, hp.econv_chans, hp.econv_chans, 5, ACT_RELU, seg=seg,
+                           key="enc_conv2")
+        gx = self.conv_gemm(x, w["blstm_wih"], w["blstm_b"], P, hp.econv_chans, 4 * E, 1, ACT_NONE, key="blstm_wih")
         h = torch.empty((P, E), dtype=torch.float32, device=self.device)
         p = _lib.BiLstmParams(n_utts=n_utts, hidden=E // 2, utt_off=dptr(utt_off), gx=dptr(gx), whh=dptr(w["blstm_whh"]),
                               out=dptr(h), group=8 if n_utts >= 8 else 1)
@@ -96,9 +111,10 @@ class Engine:
         """variance_predictor.py:86-93 / espnet DurationPredictor. -> (head (P,), dur int32 (P,) or None)"""
         hp, w = self.hp, self.w
         P, C = h.shape[0], hp.predictor_chans
-        x = self.conv_gemm(h, w[f"{name}_conv0_w"], w[f"{name}_conv0_b"], P, hp.eunits, C, 3, ACT_RELU, seg=seg)
+        x = self.conv_gemm(h, w[f"{name}_conv0_w"], w[f"{name}_conv0_b"], P, hp.eunits, C, 3, ACT_RELU, seg=seg,
+                           key=f"{name}_conv0")
         self.layernorm(x, w[f"{name}_ln0_g"], w[f"{name}_ln0_b"], y=x)
-        x = self.conv_gemm(x, w[f"{name}_conv1_w"], w[f"{name}_conv1_b"], P, C, C, 3, ACT_RELU, seg=seg)
+        x = self.conv_gemm(x, w[f"{name}_conv1_w"], w[f"{name}_conv1_b"], P, C, C, 3, ACT_RELU, seg=seg, key=f"{name}_conv1")
         head = torch.empty((P,), dtype=torch.float32, device=self.device)
         dur = torch.empty((P,), dtype=torch.int32, device=self.device) if want_dur else None
         self.layernorm(x, w[f"{name}_ln1_g"], w[f"{name}_ln1_b"], head_w=w[f"{name}_head_w"],
@@ -141,8 +157,8 @@ class Engine:
         hp, w = self.hp, self.w
         P, E, H, O = hn.shape[0], hp.eunits, hp.dunits, hp.odim
         with self.stage("decoder_hoist"):
-            g0h = self.conv_gemm(hn, w["dec_g0h_w"], w["dec_g0h_b"], P, E, 4 * H, 1, ACT_NONE)
-            y0h = self.conv_gemm(hn, w["dec_y0h_w"], None, P, E, O, 1, ACT_NONE)
+            g0h = self.conv_gemm(hn, w["dec_g0h_w"], w["dec_g0h_b"], P, E, 4 * H, 1, ACT_NONE, key="dec_g0h")
+            y0h = self.conv_gemm(hn, w["dec_y0h_w"], None, P, E, O, 1, ACT_NONE, key="dec_y0h")
         cstate = torch.empty((2, P, H), dtype=torch.float32, device=self.device)
         before = torch.empty((max(n_frames, 1), O), dtype=torch.float32, device=self.device)
         if tile_rows is None:
@@ -161,11 +177,13 @@ class Engine:
     def postnet(self, before, fseg, n_frames):
         hp, w = self.hp, self.w
         O, C = hp.odim, hp.postnet_chans
-        x = self.conv_gemm(before, w["post_conv0_w"], w["post_conv0_b"], n_frames, O, C, 5, ACT_TANH, seg=fseg)
+        x = self.conv_gemm(before, w["post_conv0_w"], w["post_conv0_b"], n_frames, O, C, 5, ACT_TANH, seg=fseg,
+                           key="post_conv0")
         for l in (1, 2, 3):
-            x = self.conv_gemm(x, w[f"post_conv{l}_w"], w[f"post_conv{l}_b"], n_frames, C, C, 5, ACT_TANH, seg=fseg)
+            x = self.conv_gemm(x, w[f"post_conv{l}_w"], w[f"post_conv{l}_b"], n_frames, C, C, 5, ACT_TANH, seg=fseg,
+                               key=f"post_conv{l}")
         return self.conv_gemm(x, w["post_conv4_w"], w["post_conv4_b"], n_frames, C, O, 5, ACT_NONE, seg=fseg,
-                              residual=before)
+                              residual=before, key="post_conv4")
 
     # ------------------------------------------------------------------ whole pass
     def upload(self, plan: BatchPlan):

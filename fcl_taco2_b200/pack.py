@@ -83,3 +83,46 @@ def pack_fp32(sd, hp: HParams) -> dict:
             {k: f(k) for k in sd if k.startswith(f"dec.postnet.postnet.{l}.")},
             f"dec.postnet.postnet.{l}.0.weight", f"dec.postnet.postnet.{l}.1")
     return out
+
+
+# ----------------------------------------------------------------------------- bf16 tensor-core packing
+def choose_ntile(cout: int) -> int:
+    """Largest multiple of 16 that divides cout and is <= 256."""
+    for nt in range(256, 15, -16):
+        if cout % nt == 0:
+            return nt
+    raise ValueError(f"cout={cout} has no tile width that is a multiple of 16")
+
+
+def choose_kstage(cin: int) -> int:
+    for ks in (64, 80, 48, 32, 16):
+        if cin % ks == 0:
+            return ks
+    raise ValueError(f"cin={cin} must be a multiple of 16")
+
+
+def pack_conv_bf16(w: torch.Tensor, ntile: int | None = None, kstage: int | None = None):
+    """(taps, cin, cout) fp32 -> bf16 blocks [cout/ntile][taps*cin/kstage][kstage/8][ntile][8]
+    (UMMA K-major no-swizzle core-matrix image of each (ntile x kstage) B stage; csrc/umma.cuh).
+    -> (flat bf16 tensor, ntile, kstage)"""
+    taps, cin, cout = w.shape
+    ntile = ntile or choose_ntile(cout)
+    kstage = kstage or choose_kstage(cin)
+    assert cout % ntile == 0 and cin % kstage == 0 and kstage % 16 == 0
+    x = w.reshape(taps, cin // kstage, kstage // 8, 8, cout // ntile, ntile)      # t, kc, k8, j, nt, n
+    x = x.permute(4, 0, 1, 2, 5, 3).contiguous()                                   # nt, t, kc, k8, n, j
+    return x.to(torch.bfloat16).reshape(-1).contiguous(), ntile, kstage
+
+
+GEMM_KEYS = ["enc_conv0", "enc_conv1", "enc_conv2", "blstm_wih", "dur_conv0", "dur_conv1", "pitch_conv0", "pitch_conv1",
+             "energy_conv0", "energy_conv1", "dec_g0h", "dec_y0h", "post_conv0", "post_conv1", "post_conv2",
+             "post_conv3", "post_conv4"]
+
+
+def pack_bf16(packed_fp32: dict) -> dict:
+    """bf16 tensor-core operands for every conv/linear GEMM, from the fp32 packed dict."""
+    out = {}
+    for key in GEMM_KEYS:
+        w = packed_fp32[key if key == "blstm_wih" else key + "_w"]
+        out[key] = pack_conv_bf16(w)
+    return out

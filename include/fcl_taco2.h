@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 3
+#define FCL_ABI_VERSION 4
 
 enum {
   FCL_OK = 0,
@@ -103,6 +103,30 @@ typedef struct {
   int32_t act;               /* FCL_ACT_*                                                  */
 } FclConvGemmParams;
 int fcl_conv_gemm_f32(const FclConvGemmParams* p, void* stream);
+
+/* Tensor-core form of the same contract (tcgen05, bf16 operands, fp32 accumulate in TMEM, fp32 activations
+ * in HBM). `w_packed` holds bf16 weights pre-tiled as UMMA core matrices:
+ *   [cout/ntile][taps*cin/kstage][kstage/8][ntile][8]   (see fcl_taco2_b200/pack.py: pack_conv_bf16)
+ * so that one pipeline stage of the B operand is one contiguous bulk copy.
+ */
+typedef struct {
+  int32_t rows, cin, cout, taps;
+  const float* a;
+  int32_t lda;
+  const int64_t* gather;
+  const int32_t* seg_lo;
+  const int32_t* seg_hi;
+  const void* w_packed;      /* bf16, layout above                                         */
+  int32_t ntile;             /* output columns per CTA: multiple of 16, <= 256, divides cout */
+  int32_t kstage;            /* K per pipeline stage: multiple of 16, <= 80, divides cin    */
+  const float* bias;
+  const float* residual;
+  int32_t ldr;
+  float* out;
+  int32_t ldo;
+  int32_t act;
+} FclConvGemmBf16Params;
+int fcl_conv_gemm_bf16(const FclConvGemmBf16Params* p, void* stream);
 
 /* ---------------------------------------------------------------- LayerNorm (+ optional head)
  * y = LayerNorm_C(x) * gamma + beta, eps 1e-12 (espnet LayerNorm, variance_predictor.py:62).
