@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -36,8 +36,9 @@ class ConvGemmParams(C.Structure):
 
 class ConvGemmBf16Params(C.Structure):
     _fields_ = [("rows", i32), ("cin", i32), ("cout", i32), ("taps", i32), ("a", ptr), ("lda", i32),
-                ("gather", ptr), ("seg_lo", ptr), ("seg_hi", ptr), ("w_packed", ptr), ("ntile", i32), ("kstage", i32),
-                ("bias", ptr), ("residual", ptr), ("ldr", i32), ("out", ptr), ("ldo", i32), ("act", i32)]
+                ("gather", ptr), ("row_gather", ptr), ("seg_lo", ptr), ("seg_hi", ptr), ("w_packed", ptr),
+                ("ntile", i32), ("kstage", i32), ("bias", ptr), ("residual", ptr), ("ldr", i32), ("out", ptr),
+                ("ldo", i32), ("act", i32), ("out_layout", i32)]
 
 
 class LayerNormParams(C.Structure):
@@ -63,8 +64,16 @@ class DecoderParams(C.Structure):
                 ("zoneout", f32), ("dropout_p", f32), ("dropout_seed", u64), ("tile_rows", i32)]
 
 
+class DecoderBf16Params(C.Structure):
+    _fields_ = [("n_rows", i32), ("n_tiles", i32), ("n_slots", i32), ("dunits", i32), ("prenet_units", i32),
+                ("odim", i32), ("order", ptr), ("dur", ptr), ("frame_off", ptr), ("row_utt", ptr), ("row_phone", ptr),
+                ("g0h_t", ptr), ("y0h_t", ptr), ("w_stream", ptr), ("bp0", ptr), ("bp1", ptr), ("wpos", ptr),
+                ("b1", ptr), ("act_ws", ptr), ("c_ws", ptr), ("before", ptr), ("zoneout", f32), ("dropout_p", f32),
+                ("dropout_seed", u64)]
+
+
 STRUCTS = [LenRegParams, FrameMapParams, ConvGemmParams, LayerNormParams, EmbedAddParams, BiLstmParams,
-           DecoderParams, ConvGemmBf16Params]
+           DecoderParams, ConvGemmBf16Params, DecoderBf16Params]
 
 ENTRY_POINTS = {
     "fcl_len_reg_scan": LenRegParams,
@@ -75,8 +84,10 @@ ENTRY_POINTS = {
     "fcl_bilstm_f32": BiLstmParams,
     "fcl_decoder_f32": DecoderParams,
     "fcl_conv_gemm_bf16": ConvGemmBf16Params,
+    "fcl_decoder_bf16": DecoderBf16Params,
 }
-PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_last_error", "fcl_sm_count", "fcl_struct_size"]
+PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_last_error", "fcl_sm_count", "fcl_struct_size",
+                 "fcl_decoder_bf16_workspace"]
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 MAX_DURATION = 1023
@@ -113,6 +124,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(st), C.c_void_p]
+    lib.fcl_decoder_bf16_workspace.restype = C.c_int
+    lib.fcl_decoder_bf16_workspace.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 
@@ -128,3 +141,12 @@ def call(name: str, params, stream: int):
 def dptr(t):
     """Device pointer of a torch tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
+
+
+def decoder_bf16_workspace(prenet_units: int, dunits: int):
+    """-> (activation-scratch bytes per CTA slot, cell-state floats per CTA slot)."""
+    a, c = C.c_int64(), C.c_int64()
+    rc = load().fcl_decoder_bf16_workspace(prenet_units, dunits, C.byref(a), C.byref(c))
+    if rc != 0:
+        raise FclError("fcl_decoder_bf16_workspace failed")
+    return a.value, c.value

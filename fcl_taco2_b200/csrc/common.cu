@@ -44,6 +44,7 @@ extern "C" int fcl_struct_size(int which) {
     case 5: return (int)sizeof(FclBiLstmParams);
     case 6: return (int)sizeof(FclDecoderParams);
     case 7: return (int)sizeof(FclConvGemmBf16Params);
+    case 8: return (int)sizeof(FclDecoderBf16Params);
     default: return -1;
   }
 }

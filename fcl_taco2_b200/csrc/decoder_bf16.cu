@@ -1,0 +1,373 @@
+// K4 (tensor-core path): persistent decoder step loop on tcgen05.
+// Reference: nets/modules/decoder_sa.py:577-617 (loop), :146-158 (Prenet, always-on dropout),
+// :63-96 (ZoneOutCell around torch.nn.LSTMCell), :398 (feat_out), fused with the ragged gather :619-630.
+//
+// One CTA owns a tile of 128 duration-sorted phoneme rows for all of their steps (rows are independent, so
+// no inter-CTA communication exists). Per step it runs five dependent GEMM phases on the tensor cores
+//   P0 prenet.0 [128 x 80(->128)] x [256]      P1 prenet.1 [128 x 256] x [256]
+//   L0 gates of cell 0: [x2 | z0] (K = 256 + H) x 4H      L1 gates of cell 1: [z0' | z1] (K = 2H) x 4H
+//   F  feat_out: z1' (K = H) x 80
+// with bf16 operands, fp32 accumulators in TMEM (two 256-column buffers: the epilogue of chunk j overlaps
+// the MMAs of chunk j+1), fp32 cell state. Weights (bf16, pre-tiled as UMMA core matrices, in consumption
+// order) and the activation operands stream through a 4-stage shared-memory ring with cp.async.bulk;
+// the activation operands of a tile (x0,x1,x2,z0,z1 as bf16 core-matrix images) live in a per-CTA global
+// scratch that stays L2-resident, written by the epilogue warps and re-read by the bulk copies
+// (generic->async proxy fence + mbarrier hand-over).
+//
+// Warp roles (384 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-11 = epilogue (TMEM lane quarter = warp % 4; warps 4-7 take the low half of a chunk's columns,
+// warps 8-11 the high half). Gate columns are interleaved (unit*4 + {i,f,g,o}) so one thread owns whole cells.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace fcl {
+using namespace umma;
+
+constexpr int kDbThreads = 384;
+constexpr int kDbStages = 4;
+constexpr uint32_t kABytes = 128u * 64u * 2u;           // one A stage: 128 rows x 64 k (bf16)
+constexpr uint32_t kBBytesMax = 256u * 64u * 2u;        // one B stage: up to 256 cols x 64 k
+constexpr uint32_t kStageBytes = kABytes + kBBytesMax;  // 48 KB
+constexpr int kEpiThreads = 256;
+
+struct DbShared {
+  uint64_t full[kDbStages], empty[kDbStages];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t a_ready[5];        // x0, x1, x2, z0', z1' operand images complete (epilogue -> producer)
+  uint32_t tmem_base;
+  int steps;
+};
+
+// activation scratch of one CTA slot (bytes)
+__host__ __device__ inline size_t db_x0_off() { return 0; }                                   // K padded to 128
+__host__ __device__ inline size_t db_x1_off() { return 128 * 128 * 2; }
+__host__ __device__ inline size_t db_x2_off(int U) { return db_x1_off() + (size_t)U * 128 * 2; }
+__host__ __device__ inline size_t db_z_off(int U, int H, int which /*0..3: z0a z0b z1a z1b*/) {
+  return db_x2_off(U) + (size_t)U * 128 * 2 + (size_t)which * H * 128 * 2;
+}
+__host__ __device__ inline size_t db_act_bytes(int U, int H) { return db_z_off(U, H, 4); }
+
+__global__ void __launch_bounds__(kDbThreads, 1)
+decoder_bf16_kernel(FclDecoderBf16Params p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ DbShared sh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = p.dunits, U = p.prenet_units, O = p.odim;
+  const int H4 = 4 * H;
+  const int kU = U / 64, kH = H / 64;               // K stages of the prenet / hidden operands
+  const int gate_chunks = H4 / 256;
+  uint8_t* act = reinterpret_cast<uint8_t*>(p.act_ws) + (size_t)blockIdx.x * db_act_bytes(U, H);
+  float* cws = p.c_ws + (size_t)blockIdx.x * 2 * H * 128;
+
+  if (tid == 0) {
+    for (int s = 0; s < kDbStages; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&sh.tmem_full[b], 1); mbar_init(&sh.tmem_empty[b], kEpiThreads); }
+    for (int i = 0; i < 5; ++i) mbar_init(&sh.a_ready[i], kEpiThreads);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&sh.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+
+  // byte size of one B stage per phase (P0, P1, L0, L1 use 256 columns; F uses O columns)
+  const uint32_t b_bytes_wide = 256u * 64u * 2u, b_bytes_feat = (uint32_t)O * 64u * 2u;
+
+  if (warp == 0) {
+    // ================================================================ producer
+    if (elect_one()) {
+      uint32_t stage = 0, sphase = 0;                 // ring position / parity
+      uint32_t rdy[5] = {0, 0, 0, 0, 0};              // parity of each a_ready barrier
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
+        for (int m = 0; m < steps; ++m) {
+          const int zp = m & 1;
+          const uint8_t* z0cur = act + db_z_off(U, H, zp), *z0new = act + db_z_off(U, H, zp ^ 1);
+          const uint8_t* z1cur = act + db_z_off(U, H, 2 + zp), *z1new = act + db_z_off(U, H, 2 + (zp ^ 1));
+          const uint8_t* wptr = reinterpret_cast<const uint8_t*>(p.w_stream);
+          for (int phase = 0; phase < 5; ++phase) {
+            mbar_wait(&sh.a_ready[phase], rdy[phase]);
+            rdy[phase] ^= 1u;
+            const int nchunks = (phase == 2 || phase == 3) ? gate_chunks : 1;
+            const int kst = phase == 0 ? 2 : phase == 1 ? kU : phase == 2 ? kU + kH : phase == 3 ? 2 * kH : kH;
+            const uint32_t bb = phase == 4 ? b_bytes_feat : b_bytes_wide;
+            for (int c = 0; c < nchunks; ++c) {
+              for (int ks = 0; ks < kst; ++ks) {
+                const uint8_t* asrc;
+                if (phase == 0) asrc = act + db_x0_off() + (size_t)ks * kABytes;
+                else if (phase == 1) asrc = act + db_x1_off() + (size_t)ks * kABytes;
+                else if (phase == 2) asrc = ks < kU ? act + db_x2_off(U) + (size_t)ks * kABytes : z0cur + (size_t)(ks - kU) * kABytes;
+                else if (phase == 3) asrc = ks < kH ? z0new + (size_t)ks * kABytes : z1cur + (size_t)(ks - kH) * kABytes;
+                else asrc = z1new + (size_t)ks * kABytes;
+                mbar_wait(&sh.empty[stage], sphase ^ 1u);
+                mbar_arrive_expect_tx(&sh.full[stage], kABytes + bb);
+                uint8_t* st = smem + (size_t)stage * kStageBytes;
+                bulk_g2s(st, asrc, kABytes, &sh.full[stage]);
+                bulk_g2s(st + kABytes, wptr, bb, &sh.full[stage]);
+                wptr += bb;
+                if (++stage == kDbStages) { stage = 0; sphase ^= 1u; }
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (elect_one()) {
+      uint32_t stage = 0, sphase = 0;
+      uint32_t chunk_ctr = 0;                          // accumulator buffer = chunk_ctr & 1
+      const uint32_t idesc_wide = idesc_bf16_f32(128u, 256u), idesc_feat = idesc_bf16_f32(128u, (uint32_t)O);
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
+        for (int m = 0; m < steps; ++m) {
+          for (int phase = 0; phase < 5; ++phase) {
+            const int nchunks = (phase == 2 || phase == 3) ? gate_chunks : 1;
+            const int kst = phase == 0 ? 2 : phase == 1 ? kU : phase == 2 ? kU + kH : phase == 3 ? 2 * kH : kH;
+            const uint32_t ncols = phase == 4 ? (uint32_t)O : 256u;
+            const uint32_t idesc = phase == 4 ? idesc_feat : idesc_wide;
+            const uint32_t b_lbo = ncols * 16u;
+            for (int c = 0; c < nchunks; ++c) {
+              const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
+              mbar_wait(&sh.tmem_empty[buf], (use & 1u) ^ 1u);
+              tc_fence_after();
+              const uint32_t d_tmem = tmem + buf * 256u;
+              for (int ks = 0; ks < kst; ++ks) {
+                mbar_wait(&sh.full[stage], sphase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes);
+                const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = smem_desc(a_addr + (uint32_t)k * 4096u, 2048u, 128u);
+                  const uint64_t bd = smem_desc(b_addr + (uint32_t)k * 2u * b_lbo, b_lbo, 128u);
+                  mma_bf16_ss(d_tmem, ad, bd, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+                }
+                mma_commit(&sh.empty[stage]);
+                if (++stage == kDbStages) { stage = 0; sphase ^= 1u; }
+              }
+              mma_commit(&sh.tmem_full[buf]);
+              ++chunk_ctr;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ================================================================ epilogue (256 threads)
+    const int q = warp & 3, hsel = (warp - 4) >> 2;
+    const int r = q * 32 + lane;                       // row within the tile == TMEM lane
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t chunk_ctr = 0;
+    const float zo = p.zoneout, zk = 1.0f - p.zoneout;
+    const bool use_drop = p.dropout_p > 0.f;
+    const uint32_t drop_thr = dropout_threshold(p.dropout_p);
+    const float drop_scale = use_drop ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int sidx = tile * 128 + r;
+      int row = -1, d = 0, foff = 0, utt = 0, ph = 0;
+      if (sidx < p.n_rows) {
+        row = p.order[sidx];
+        d = min(max(p.dur[row], 0), FCL_MAX_DURATION);
+        foff = p.frame_off[row];
+        utt = p.row_utt[row];
+        ph = p.row_phone[row];
+      }
+      const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
+      if (steps == 0) continue;
+      // ---- tile init: zero x0 (all 16 k-chunks) and the "current" z images; this thread's half of the chunks
+      {
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        for (int kc = hsel; kc < 16; kc += 2) *reinterpret_cast<uint4*>(act + db_x0_off() + ((size_t)kc * 128 + r) * 16) = z4;
+        for (int kc = hsel; kc < H / 8; kc += 2) {
+          *reinterpret_cast<uint4*>(act + db_z_off(U, H, 0) + ((size_t)kc * 128 + r) * 16) = z4;
+          *reinterpret_cast<uint4*>(act + db_z_off(U, H, 2) + ((size_t)kc * 128 + r) * 16) = z4;
+        }
+        fence_proxy_async_all();
+        mbar_arrive(&sh.a_ready[0]);
+      }
+      const float* g0t = p.g0h_t + (size_t)tile * H4 * 128;     // [H][128][4] fp32
+      const float* y0t = p.y0h_t + (size_t)tile * O * 128;      // [O/4][128][4]
+
+      for (int m = 0; m < steps; ++m) {
+        const int zp = m & 1;
+        uint8_t* z0cur = act + db_z_off(U, H, zp), *z0new = act + db_z_off(U, H, zp ^ 1);
+        uint8_t* z1cur = act + db_z_off(U, H, 2 + zp), *z1new = act + db_z_off(U, H, 2 + (zp ^ 1));
+        const float pos = (row >= 0 && m < d) ? __fdiv_rn((float)m, (float)d) : 0.f;
+
+        // ---------------- P0, P1: prenet layers (bias, ReLU, dropout) -> x1 / x2 images
+#pragma unroll 1
+        for (int layer = 0; layer < 2; ++layer) {
+          const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
+          mbar_wait(&sh.tmem_full[buf], use & 1u);
+          tc_fence_after();
+          const float* bias = layer == 0 ? p.bp0 : p.bp1;
+          uint8_t* dst = act + (layer == 0 ? db_x1_off() : db_x2_off(U));
+#pragma unroll 1
+          for (int g = 0; g < 4; ++g) {
+            float v[32];
+            const int col0 = hsel * 128 + g * 32;
+            tmem_ld32(lane_addr + buf * 256u + (uint32_t)col0, v);
+#pragma unroll
+            for (int qd = 0; qd < 8; ++qd) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0) + qd);
+              float x[4] = {fmaxf(v[4 * qd] + b4.x, 0.f), fmaxf(v[4 * qd + 1] + b4.y, 0.f),
+                            fmaxf(v[4 * qd + 2] + b4.z, 0.f), fmaxf(v[4 * qd + 3] + b4.w, 0.f)};
+              if (use_drop) {
+                const Philox4 rnd = dropout_words(p.dropout_seed, (uint32_t)utt, (uint32_t)ph, (uint32_t)m,
+                                                  (uint32_t)layer, (uint32_t)((col0 >> 2) + qd));
+                x[0] = rnd.x >= drop_thr ? x[0] * drop_scale : 0.f;
+                x[1] = rnd.y >= drop_thr ? x[1] * drop_scale : 0.f;
+                x[2] = rnd.z >= drop_thr ? x[2] * drop_scale : 0.f;
+                x[3] = rnd.w >= drop_thr ? x[3] * drop_scale : 0.f;
+              }
+              v[4 * qd] = x[0]; v[4 * qd + 1] = x[1]; v[4 * qd + 2] = x[2]; v[4 * qd + 3] = x[3];
+            }
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) {
+              uint4 w;
+              w.x = pack_bf16(v[8 * k8], v[8 * k8 + 1]); w.y = pack_bf16(v[8 * k8 + 2], v[8 * k8 + 3]);
+              w.z = pack_bf16(v[8 * k8 + 4], v[8 * k8 + 5]); w.w = pack_bf16(v[8 * k8 + 6], v[8 * k8 + 7]);
+              *reinterpret_cast<uint4*>(dst + ((size_t)((col0 >> 3) + k8) * 128 + r) * 16) = w;
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&sh.tmem_empty[buf]);
+          ++chunk_ctr;
+          fence_proxy_async_all();
+          mbar_arrive(&sh.a_ready[1 + layer]);
+        }
+
+        // ---------------- L0, L1: zoneout LSTM cells
+#pragma unroll 1
+        for (int layer = 0; layer < 2; ++layer) {
+          const uint8_t* zcur = layer == 0 ? z0cur : z1cur;
+          uint8_t* znew = layer == 0 ? z0new : z1new;
+          float* cl = cws + (size_t)layer * H * 128;
+#pragma unroll 1
+          for (int c = 0; c < gate_chunks; ++c) {
+            const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
+            mbar_wait(&sh.tmem_full[buf], use & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int g = 0; g < 4; ++g) {
+              float v[32];
+              tmem_ld32(lane_addr + buf * 256u + (uint32_t)(hsel * 128 + g * 32), v);
+              const int u0 = c * 64 + hsel * 32 + g * 8;           // first of 8 hidden units
+              const uint4 zraw = *reinterpret_cast<const uint4*>(zcur + ((size_t)(u0 >> 3) * 128 + r) * 16);
+              const uint32_t zr[4] = {zraw.x, zraw.y, zraw.z, zraw.w};
+              float zn[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int u = u0 + j;
+                float4 add;
+                if (layer == 0) {
+                  add = __ldg(reinterpret_cast<const float4*>(g0t + ((size_t)u * 128 + r) * 4));
+                  const float4 wp = __ldg(reinterpret_cast<const float4*>(p.wpos + 4 * u));
+                  add.x = fmaf(pos, wp.x, add.x); add.y = fmaf(pos, wp.y, add.y);
+                  add.z = fmaf(pos, wp.z, add.z); add.w = fmaf(pos, wp.w, add.w);
+                } else {
+                  add = __ldg(reinterpret_cast<const float4*>(p.b1 + 4 * u));
+                }
+                const float ig = sigmoid_fast(v[4 * j] + add.x), fg = sigmoid_fast(v[4 * j + 1] + add.y);
+                const float gg = tanh_fast(v[4 * j + 2] + add.z), og = sigmoid_fast(v[4 * j + 3] + add.w);
+                const float cold = m == 0 ? 0.f : cl[(size_t)u * 128 + r];
+                const float cn = fmaf(fg, cold, ig * gg);
+                const float hn = og * tanh_fast(cn);
+                const uint32_t zw = zr[j >> 1];
+                const float zold = __uint_as_float((j & 1) ? (zw & 0xFFFF0000u) : (zw << 16));
+                zn[j] = fmaf(zo, zold, zk * hn);                    // decoder_sa.py:95-96 (eval blend)
+                cl[(size_t)u * 128 + r] = fmaf(zo, cold, zk * cn);
+              }
+              uint4 w;
+              w.x = pack_bf16(zn[0], zn[1]); w.y = pack_bf16(zn[2], zn[3]);
+              w.z = pack_bf16(zn[4], zn[5]); w.w = pack_bf16(zn[6], zn[7]);
+              *reinterpret_cast<uint4*>(znew + ((size_t)(u0 >> 3) * 128 + r) * 16) = w;
+            }
+            tc_fence_before();
+            mbar_arrive(&sh.tmem_empty[buf]);
+            ++chunk_ctr;
+          }
+          fence_proxy_async_all();
+          mbar_arrive(&sh.a_ready[3 + layer]);
+        }
+
+        // ---------------- F: feat_out (+ hoisted h term) -> output frame (ragged store) and x0 image
+        {
+          const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
+          mbar_wait(&sh.tmem_full[buf], use & 1u);
+          tc_fence_after();
+          // 16-column groups: warps with hsel == 0 take groups 0,2,4.., hsel == 1 take 1,3,..
+          for (int g = hsel; g < O / 16; g += 2) {
+            float v[16];
+            tmem_ld16(lane_addr + buf * 256u + (uint32_t)(g * 16), v);
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+              const float4 y0 = __ldg(reinterpret_cast<const float4*>(y0t + ((size_t)(g * 4 + qd) * 128 + r) * 4));
+              v[4 * qd] += y0.x; v[4 * qd + 1] += y0.y; v[4 * qd + 2] += y0.z; v[4 * qd + 3] += y0.w;
+            }
+            if (row >= 0 && m < d) {                               // exhausted rows are masked (decoder_sa.py:625-629)
+              float4* o = reinterpret_cast<float4*>(p.before + ((size_t)foff + m) * O + g * 16);
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) o[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+            }
+#pragma unroll
+            for (int k8 = 0; k8 < 2; ++k8) {
+              uint4 w;
+              w.x = pack_bf16(v[8 * k8], v[8 * k8 + 1]); w.y = pack_bf16(v[8 * k8 + 2], v[8 * k8 + 3]);
+              w.z = pack_bf16(v[8 * k8 + 4], v[8 * k8 + 5]); w.w = pack_bf16(v[8 * k8 + 6], v[8 * k8 + 7]);
+              *reinterpret_cast<uint4*>(act + db_x0_off() + ((size_t)(g * 2 + k8) * 128 + r) * 16) = w;
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&sh.tmem_empty[buf]);
+          ++chunk_ctr;
+          if (m + 1 < steps) {
+            fence_proxy_async_all();
+            mbar_arrive(&sh.a_ready[0]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace fcl
+
+extern "C" int fcl_decoder_bf16_workspace(int32_t prenet_units, int32_t dunits, int64_t* act_bytes_per_slot,
+                                          int64_t* c_floats_per_slot) {
+  if (!act_bytes_per_slot || !c_floats_per_slot) return FCL_EINVAL;
+  *act_bytes_per_slot = (int64_t)fcl::db_act_bytes(prenet_units, dunits);
+  *c_floats_per_slot = (int64_t)2 * dunits * 128;
+  return FCL_OK;
+}
+
+extern "C" int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream) {
+  using namespace fcl;
+  FCL_REQUIRE(p && p->order && p->dur && p->frame_off && p->row_utt && p->row_phone && p->g0h_t && p->y0h_t &&
+                  p->w_stream && p->bp0 && p->bp1 && p->wpos && p->b1 && p->act_ws && p->c_ws && p->before,
+              "null pointer");
+  FCL_REQUIRE(p->n_rows > 0 && p->n_tiles == (p->n_rows + 127) / 128, "n_tiles must be ceil(n_rows / 128)");
+  FCL_REQUIRE(p->prenet_units == 256, "prenet_units must be 256 (one 256-column chunk)");
+  FCL_REQUIRE(p->dunits % 64 == 0 && p->dunits >= 64, "dunits must be a multiple of 64");
+  FCL_REQUIRE(p->odim % 16 == 0 && p->odim <= 128, "odim must be a multiple of 16, <= 128");
+  FCL_REQUIRE(p->n_slots >= 1, "n_slots must be >= 1");
+  FCL_REQUIRE(p->zoneout >= 0.f && p->zoneout < 1.f && p->dropout_p >= 0.f && p->dropout_p < 1.f, "bad rates");
+  const size_t smem = (size_t)kDbStages * kStageBytes;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(decoder_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("fcl_decoder_bf16: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
+    attr_done = true;
+  }
+  const int grid = p->n_tiles < p->n_slots ? p->n_tiles : p->n_slots;
+  decoder_bf16_kernel<<<grid, kDbThreads, smem, as_stream(stream)>>>(*p);
+  return check_launch("fcl_decoder_bf16");
+}

@@ -62,7 +62,10 @@ conv_gemm_bf16_kernel(FclConvGemmBf16Params p, int stages) {
       const int src = grow + t - half;
       const bool valid = row_ok && src >= seg_lo && src < seg_hi;
       const float* base = nullptr;
-      if (valid) base = (p.gather ? p.a + (size_t)p.gather[src] * p.lda : p.a + (size_t)src * p.lda) + kc;
+      if (valid) {
+        const size_t arow = p.gather ? (size_t)p.gather[src] : p.row_gather ? (size_t)p.row_gather[src] : (size_t)src;
+        base = p.a + arow * p.lda + kc;
+      }
       // issue all global loads of the stage before touching shared memory (memory-level parallelism)
       float4 v[20];                                   // kstage <= 80 -> 20 float4
 #pragma unroll
@@ -92,7 +95,7 @@ conv_gemm_bf16_kernel(FclConvGemmBf16Params p, int stages) {
     for (int g = 0; g < ntile / 16; ++g) {
       float acc[16];
       tmem_ld16(lane_addr + (uint32_t)(g * 16), acc);
-      if (row_ok) {
+      if (row_ok || p.out_layout == 1) {
         const int n = n0 + g * 16;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -103,11 +106,14 @@ conv_gemm_bf16_kernel(FclConvGemmBf16Params p, int stages) {
           }
           if (p.act == FCL_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
           else if (p.act == FCL_ACT_TANH) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
-          if (p.residual) {
+          if (p.residual && row_ok) {
             const float4 rr = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)grow * p.ldr + n) + q);
             o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
           }
-          reinterpret_cast<float4*>(p.out + (size_t)grow * p.ldo + n)[q] = o;
+          if (p.out_layout == 0)
+            reinterpret_cast<float4*>(p.out + (size_t)grow * p.ldo + n)[q] = o;
+          else   // tile-transposed [row tile][cout/4][128][4]: a warp stores 512 contiguous bytes
+            *reinterpret_cast<float4*>(p.out + (((size_t)blockIdx.x * (p.cout >> 2) + ((n >> 2) + q)) * 128 + r) * 4) = o;
         }
       }
     }
@@ -165,13 +171,15 @@ extern "C" int fcl_conv_gemm_bf16(const FclConvGemmBf16Params* p, void* stream) 
   FCL_REQUIRE(p->lda % 4 == 0 && p->ldo % 4 == 0 && (!p->residual || p->ldr % 4 == 0), "leading dims must be multiples of 4");
   FCL_REQUIRE(p->taps == 1 || (p->seg_lo && p->seg_hi), "taps > 1 needs segment bounds");
   const size_t stage_bytes = (size_t)(128 + p->ntile) * p->kstage * 2;
-  int stages = (int)((100 * 1024) / stage_bytes);
+  // prefer a footprint that lets two CTAs share an SM (one CTA's epilogue overlaps the other's main loop)
+  int stages = (int)((108 * 1024) / stage_bytes);
+  if (stages < 2) stages = (int)((216 * 1024) / stage_bytes);
   stages = stages > kMaxStages ? kMaxStages : stages;
   FCL_REQUIRE(stages >= 2, "tile too large for two pipeline stages");
   const size_t smem = stage_bytes * stages;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 101 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
     if (e != cudaSuccess) { set_error("fcl_conv_gemm_bf16: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
     attr_done = true;
   }

@@ -38,7 +38,10 @@ class BatchResult:
 
 
 class Engine:
-    def __init__(self, hp: HParams, packed: dict, device, precision: str = "fp32"):
+    def __init__(self, hp: HParams, packed: dict, device, precision: str = "fp32", bf16_gemms=None,
+                 bf16_decoder: bool = True):
+        """precision 'bf16': tcgen05 kernels. `bf16_gemms` (iterable of pack.GEMM_KEYS, default all) and
+        `bf16_decoder` select which parts use them -- used by the error-budget diagnostics."""
         hp.validate()
         if precision not in ("fp32", "bf16"):
             raise ValueError(f"unknown precision {precision!r}")
@@ -51,7 +54,14 @@ class Engine:
         self.wb = {}
         if precision == "bf16":
             from . import pack as _pack
-            self.wb = {k: (t.to(self.device), nt, ks) for k, (t, nt, ks) in _pack.pack_bf16(packed).items()}
+            self.wb = {k: (t.to(self.device), nt, ks) for k, (t, nt, ks) in _pack.pack_bf16(packed).items()
+                       if bf16_gemms is None or k in bf16_gemms or k in ("dec_g0h", "dec_y0h")}
+            self.bf16_decoder = bf16_decoder
+            self.dec_stream = _pack.pack_decoder_stream(packed, hp).to(self.device)
+            self.n_slots = _lib.load().fcl_sm_count()
+            act_b, c_f = _lib.decoder_bf16_workspace(hp.prenet_units, hp.dunits)
+            self.dec_act_ws = torch.empty((self.n_slots * act_b,), dtype=torch.uint8, device=self.device)
+            self.dec_c_ws = torch.empty((self.n_slots * c_f,), dtype=torch.float32, device=self.device)
         self.head_b = {s: float(packed[f"{s}_head_b"][0]) for s in ("dur", "pitch", "energy")}
         self.launches = 0
         self.stage_events = None      # when a list: (stage, start_event, stop_event) appended per stage (bench.py)
@@ -65,16 +75,18 @@ class Engine:
         self.launches += 1
 
     def conv_gemm(self, a, w, bias, rows, cin, cout, taps, act, seg=None, gather=None, residual=None, out=None,
-                  lda=None, key=None):
+                  lda=None, key=None, row_gather=None, tile_transposed=False):
         if out is None:
-            out = torch.empty((rows, cout), dtype=torch.float32, device=self.device)
+            n_out = (rows + 127) // 128 * 128 if tile_transposed else rows
+            out = torch.empty((n_out, cout), dtype=torch.float32, device=self.device)
         if key is not None and key in self.wb:
             wp, ntile, kstage = self.wb[key]
             p = _lib.ConvGemmBf16Params(rows=rows, cin=cin, cout=cout, taps=taps, a=dptr(a), lda=lda or cin,
-                                        gather=dptr(gather), seg_lo=dptr(seg[0]) if seg else None,
+                                        gather=dptr(gather), row_gather=dptr(row_gather),
+                                        seg_lo=dptr(seg[0]) if seg else None,
                                         seg_hi=dptr(seg[1]) if seg else None, w_packed=dptr(wp), ntile=ntile,
                                         kstage=kstage, bias=dptr(bias), residual=dptr(residual), ldr=cout,
-                                        out=dptr(out), ldo=cout, act=act)
+                                        out=dptr(out), ldo=cout, act=act, out_layout=1 if tile_transposed else 0)
             self._call("fcl_conv_gemm_bf16", p)
             return out
         p = _lib.ConvGemmParams(rows=rows, cin=cin, cout=cout, taps=taps, a=dptr(a), lda=lda or cin,
@@ -156,9 +168,12 @@ class Engine:
                 tile_rows=None):
         hp, w = self.hp, self.w
         P, E, H, O = hn.shape[0], hp.eunits, hp.dunits, hp.odim
+        if self.precision == "bf16" and self.bf16_decoder:
+            return self.decoder_bf16(hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p,
+                                     dropout_seed)
         with self.stage("decoder_hoist"):
-            g0h = self.conv_gemm(hn, w["dec_g0h_w"], w["dec_g0h_b"], P, E, 4 * H, 1, ACT_NONE, key="dec_g0h")
-            y0h = self.conv_gemm(hn, w["dec_y0h_w"], None, P, E, O, 1, ACT_NONE, key="dec_y0h")
+            g0h = self.conv_gemm(hn, w["dec_g0h_w"], w["dec_g0h_b"], P, E, 4 * H, 1, ACT_NONE)
+            y0h = self.conv_gemm(hn, w["dec_y0h_w"], None, P, E, O, 1, ACT_NONE)
         cstate = torch.empty((2, P, H), dtype=torch.float32, device=self.device)
         before = torch.empty((max(n_frames, 1), O), dtype=torch.float32, device=self.device)
         if tile_rows is None:
@@ -172,6 +187,27 @@ class Engine:
                                dropout_seed=dropout_seed, tile_rows=tile_rows)
         with self.stage("decoder_loop"):
             self._call("fcl_decoder_f32", p)
+        return before
+
+    def decoder_bf16(self, hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p, dropout_seed):
+        """Tensor-core decoder: hoisted terms in sorted-tile order (transposed), then the persistent tcgen05 loop."""
+        hp, w = self.hp, self.w
+        P, E, H, O = hn.shape[0], hp.eunits, hp.dunits, hp.odim
+        with self.stage("decoder_hoist"):
+            g0h = self.conv_gemm(hn, None, w["dec_g0h_b"], P, E, 4 * H, 1, ACT_NONE, key="dec_g0h", row_gather=order,
+                                 tile_transposed=True)
+            y0h = self.conv_gemm(hn, None, None, P, E, O, 1, ACT_NONE, key="dec_y0h", row_gather=order,
+                                 tile_transposed=True)
+        before = torch.empty((max(n_frames, 1), O), dtype=torch.float32, device=self.device)
+        p = _lib.DecoderBf16Params(n_rows=P, n_tiles=(P + 127) // 128, n_slots=self.n_slots, dunits=H,
+                                   prenet_units=hp.prenet_units, odim=O, order=dptr(order), dur=dptr(dur),
+                                   frame_off=dptr(frame_off), row_utt=dptr(row_utt), row_phone=dptr(row_phone),
+                                   g0h_t=dptr(g0h), y0h_t=dptr(y0h), w_stream=dptr(self.dec_stream),
+                                   bp0=dptr(w["dec_bp0"]), bp1=dptr(w["dec_bp1"]), wpos=dptr(w["dec_wpos"]),
+                                   b1=dptr(w["dec_b1"]), act_ws=dptr(self.dec_act_ws), c_ws=dptr(self.dec_c_ws),
+                                   before=dptr(before), zoneout=zoneout, dropout_p=dropout_p, dropout_seed=dropout_seed)
+        with self.stage("decoder_loop"):
+            self._call("fcl_decoder_bf16", p)
         return before
 
     def postnet(self, before, fseg, n_frames):

@@ -126,3 +126,21 @@ def pack_bf16(packed_fp32: dict) -> dict:
         w = packed_fp32[key if key == "blstm_wih" else key + "_w"]
         out[key] = pack_conv_bf16(w)
     return out
+
+
+def pack_decoder_stream(packed_fp32: dict, hp) -> torch.Tensor:
+    """bf16 weight stream of the tensor-core decoder, in the order the kernel consumes it each step
+    (csrc/decoder_bf16.cu): prenet.0 (K 80 -> 128 zero-padded) | prenet.1 | cell 0 | cell 1 | feat_out.
+    Every block is the UMMA core-matrix image of one (256-or-odim columns x 64 k) B stage."""
+    U, H, O = hp.prenet_units, hp.dunits, hp.odim
+    assert U == 256 and H % 64 == 0 and O % 16 == 0 and O <= 128
+    wp0 = torch.zeros(128, U)
+    wp0[:O] = packed_fp32["dec_wp0"]
+    parts = [
+        pack_conv_bf16(wp0.unsqueeze(0), 256, 64)[0],
+        pack_conv_bf16(packed_fp32["dec_wp1"].unsqueeze(0), 256, 64)[0],
+        pack_conv_bf16(packed_fp32["dec_w0"].unsqueeze(0), 256, 64)[0],
+        pack_conv_bf16(packed_fp32["dec_w1"].unsqueeze(0), 256, 64)[0],
+        pack_conv_bf16(packed_fp32["dec_wf"].unsqueeze(0), O, 64)[0],
+    ]
+    return torch.cat(parts).contiguous()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 4
+#define FCL_ABI_VERSION 5
 
 enum {
   FCL_OK = 0,
@@ -113,7 +113,8 @@ typedef struct {
   int32_t rows, cin, cout, taps;
   const float* a;
   int32_t lda;
-  const int64_t* gather;
+  const int64_t* gather;     /* optional: A row r is table row gather[r] (embedding ids)   */
+  const int32_t* row_gather; /* optional: A row r is row row_gather[r] of `a` (row permutation) */
   const int32_t* seg_lo;
   const int32_t* seg_hi;
   const void* w_packed;      /* bf16, layout above                                         */
@@ -125,6 +126,8 @@ typedef struct {
   float* out;
   int32_t ldo;
   int32_t act;
+  int32_t out_layout;        /* 0: row-major (rows, ldo). 1: tile-transposed [rows/128][cout/4][128][4]
+                                (what the tensor-core decoder reads; rows padded to full tiles) */
 } FclConvGemmBf16Params;
 int fcl_conv_gemm_bf16(const FclConvGemmBf16Params* p, void* stream);
 
@@ -217,6 +220,40 @@ typedef struct {
   int32_t tile_rows;         /* 16 or 32                                                   */
 } FclDecoderParams;
 int fcl_decoder_f32(const FclDecoderParams* p, void* stream);
+
+/* Tensor-core form of K4 (tcgen05; bf16 operands, fp32 accumulators in TMEM, fp32 cell state).
+ * Tiles are 128 duration-sorted rows; a persistent grid of `n_slots` CTAs walks the tiles round-robin.
+ *   g0h_t / y0h_t : hoisted terms in SORTED row order, tile-transposed [tile][cols/4][128][4] fp32
+ *                   (fcl_conv_gemm_bf16 with row_gather = order and out_layout = 1)
+ *   w_stream      : bf16 weights pre-tiled as UMMA core matrices in consumption order
+ *                   prenet.0 (K padded 80->128) | prenet.1 | cell 0 [W_ih0 prenet part ; W_hh0] |
+ *                   cell 1 [W_ih1 ; W_hh1] | feat_out (fcl_taco2_b200/pack.py: pack_decoder_stream)
+ *   act_ws / c_ws : per-slot scratch, sizes from fcl_decoder_bf16_workspace()
+ */
+typedef struct {
+  int32_t n_rows, n_tiles, n_slots, dunits, prenet_units, odim;
+  const int32_t* order;
+  const int32_t* dur;
+  const int32_t* frame_off;
+  const int32_t* row_utt;
+  const int32_t* row_phone;
+  const float* g0h_t;
+  const float* y0h_t;
+  const void* w_stream;
+  const float* bp0;          /* (U) prenet.0 bias                                          */
+  const float* bp1;          /* (U) prenet.1 bias                                          */
+  const float* wpos;         /* (4H) gate-interleaved position column of W_ih0             */
+  const float* b1;           /* (4H) gate-interleaved b_ih1 + b_hh1                        */
+  void* act_ws;              /* n_slots * act_bytes_per_slot                               */
+  float* c_ws;               /* n_slots * c_floats_per_slot                                */
+  float* before;             /* out (F, odim)                                              */
+  float zoneout;
+  float dropout_p;
+  uint64_t dropout_seed;
+} FclDecoderBf16Params;
+int fcl_decoder_bf16_workspace(int32_t prenet_units, int32_t dunits, int64_t* act_bytes_per_slot,
+                               int64_t* c_floats_per_slot);
+int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream);
 
 #ifdef __cplusplus
 }

@@ -80,3 +80,77 @@ def test_conv_gemm_bf16_matches_bf16_rounded_reference(rows, cin, cout, taps, ac
     assert torch.isfinite(got).all()
     err = float((got - ref).abs().max())
     assert err < 2e-3 * max(1.0, float(ref.abs().max())), err
+
+
+# ----------------------------------------------------------------------------- decoder / end-to-end, bf16 path
+# Stated tolerances of the tensor-core path (bf16 GEMM operands, fp32 accumulate, fp32 cell state,
+# tanh.approx activations) against the fp32 oracle, on mels of abs-mean ~1:
+DEC_MAX_ABS, DEC_MEAN_L1 = 2e-2, 3e-3       # decoder output before the postnet
+MEL_MAX_ABS, MEL_MEAN_L1 = 1.2e-1, 1.2e-2   # final mels, every GEMM in bf16 (observed <= 7.9e-2 / 8.2e-3 on the
+                                            # 500-phoneme stress case; tools/error_budget.py splits it by stage:
+                                            # the random-init postnet amplifies a 4.5e-3 decoder error ~6x)
+
+from fcl_taco2_b200 import hparams, plan as planmod, synth          # noqa: E402
+from oracle import restate                                         # noqa: E402
+from tests.conftest import golden_cases                            # noqa: E402
+from tests.helpers import weights, err, load_golden                # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def bf16_engines():
+    from fcl_taco2_b200.engine import Engine
+    out = {}
+
+    def get(kind, seed=0):
+        if (kind, seed) not in out:
+            hp = hparams.preset(kind)
+            sd = weights(kind, seed)
+            out[(kind, seed)] = (Engine(hp, pack.pack_fp32(sd, hp), "cuda:0", "bf16"), sd, hp)
+        return out[(kind, seed)]
+    return get
+
+
+@pytest.mark.parametrize("kind,n_utts", [("S", 3), ("S", 9), ("T", 2)])
+@pytest.mark.parametrize("drop", [0.0, 0.5])
+def test_decoder_bf16_steps(bf16_engines, kind, n_utts, drop):
+    eng, sd, hp = bf16_engines(kind)
+    xs, ds = synth.synth_batch(n_utts, 9, fixed_len=47)          # 141 / 423 / 94 rows: partial tiles, >1 tile
+    pl = planmod.make_plan(xs, ds)
+    d, _ = eng.upload(pl)
+    hn = torch.randn(pl.n_rows, hp.eunits, generator=torch.Generator().manual_seed(5))
+    frame_off, ufo, order, totals = eng.len_reg_scan(d["dur"], d["utt_off"], pl.n_utts)
+    F_ = int(pl.dur.sum())
+    before = eng.decoder(hn.cuda(), d["dur"], frame_off, order, d["row_utt"], d["row_phone"], F_, 0.1, drop, 99)
+    torch.cuda.synchronize()
+    dur = torch.from_numpy(pl.dur.astype(np.int64))
+    steps = restate.decoder_steps(sd, hn, restate.position_table(dur), int(dur.max()), 0.1,
+                                  restate.Dropout(drop, 99), pl.row_utt, pl.row_phone)
+    row, step, _ = restate.frame_map(dur.numpy())
+    ref = steps[torch.from_numpy(row), torch.from_numpy(step)]
+    assert torch.isfinite(before).all()
+    mx, mean = err(before.cpu(), ref)
+    print(f"decoder bf16 {kind} drop={drop}: max-abs {mx:.3e} mean-L1 {mean:.3e}")
+    assert mx < DEC_MAX_ABS and mean < DEC_MEAN_L1, (mx, mean)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_e2e_bf16_against_reference_golden(name):
+    from fcl_taco2_b200 import model as M
+    g = load_golden(name)
+    m = M.from_preset(g["kind"], seed=None, device="cpu", precision="bf16")
+    m.load_state_dict(weights(g["kind"], g["weight_seed"]))
+    m = m.to("cuda:0").set_prenet_dropout(rate=g["dropout_rate"], seed=g["dropout_seed"])
+    out = m.inference(torch.from_numpy(g["x"]), None, dur=g["dur"], dropout_utt_index=g["utt_index"])
+    mx, mean = err(out.cpu(), g["out"])
+    print(f"e2e bf16 {name}: max-abs {mx:.3e} mean-L1 {mean:.3e}")
+    assert mx < MEL_MAX_ABS and mean < MEL_MEAN_L1, (mx, mean)
+
+
+def test_bf16_batched_equals_looped():
+    from fcl_taco2_b200 import model as M
+    m = M.from_preset("S", seed=3, device="cuda:0", precision="bf16").set_prenet_dropout(rate=0.5, seed=8)
+    xs, ds = synth.synth_batch(5, 77)
+    outs = m.inference_batch(xs, durs=ds)
+    for i in range(len(xs)):
+        single = m.inference(torch.from_numpy(xs[i]), None, dur=ds[i], dropout_utt_index=i)
+        assert torch.equal(single, outs[i])
