@@ -47,6 +47,33 @@ __host__ __device__ inline size_t db_z_off(int U, int H, int which /*0..3: z0a z
 }
 __host__ __device__ inline size_t db_act_bytes(int U, int H) { return db_z_off(U, H, 4); }
 
+// tile visited at round `tk` by this CTA: boustrophedon over duration-sorted tiles (longest first), so every
+// CTA gets a similar sum of steps. -1 when done.
+__device__ __forceinline__ int db_tile(int tk, int n_tiles) {
+  const int G = gridDim.x, b = blockIdx.x;
+  const int t = tk * G + ((tk & 1) ? (G - 1 - b) : b);
+  if (tk * G >= n_tiles) return -1;
+  return t < n_tiles ? t : -2;          // -2: no tile for this CTA in the last, partial round
+}
+
+// global operands of one gate work item (4 hidden units of one row)
+struct GatePref {
+  float4 add[4];      // hoisted gate pre-activation (cell 0) or bias (cell 1), gates i,f,g,o
+  float cold[4];      // previous cell state
+  uint2 z;            // previous zoned-out hidden state, 4 x bf16
+};
+
+__device__ __forceinline__ void gate_prefetch(GatePref& pf, int layer, int u0, int r, int m, const float* __restrict__ g0t,
+                                              const float* __restrict__ b1, const float* cl, const uint8_t* zcur) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    pf.add[j] = layer == 0 ? __ldg(reinterpret_cast<const float4*>(g0t + ((size_t)(u0 + j) * 128 + r) * 4))
+                           : __ldg(reinterpret_cast<const float4*>(b1 + 4 * (u0 + j)));
+    pf.cold[j] = m == 0 ? 0.f : __ldcg(cl + (size_t)(u0 + j) * 128 + r);
+  }
+  pf.z = __ldcg(reinterpret_cast<const uint2*>(zcur + ((size_t)(u0 >> 3) * 128 + r) * 16 + (u0 & 4) * 2));
+}
+
 __global__ void __launch_bounds__(kDbThreads, 1)
 decoder_bf16_kernel(FclDecoderBf16Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -79,7 +106,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
     if (elect_one()) {
       uint32_t stage = 0, sphase = 0;                 // ring position / parity
       uint32_t rdy[5] = {0, 0, 0, 0, 0};              // parity of each a_ready barrier
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int tk = 0, tile; (tile = db_tile(tk, p.n_tiles)) >= 0; ++tk) {
         const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
         for (int m = 0; m < steps; ++m) {
           const int zp = m & 1;
@@ -120,7 +147,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
       uint32_t stage = 0, sphase = 0;
       uint32_t chunk_ctr = 0;                          // accumulator buffer = chunk_ctr & 1
       const uint32_t idesc_wide = idesc_bf16_f32(128u, 256u), idesc_feat = idesc_bf16_f32(128u, (uint32_t)O);
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int tk = 0, tile; (tile = db_tile(tk, p.n_tiles)) >= 0; ++tk) {
         const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
         for (int m = 0; m < steps; ++m) {
           for (int phase = 0; phase < 5; ++phase) {
@@ -167,7 +194,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
     const uint32_t drop_thr = dropout_threshold(p.dropout_p);
     const float drop_scale = use_drop ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
 
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    for (int tk = 0, tile; (tile = db_tile(tk, p.n_tiles)) >= 0; ++tk) {
       const int sidx = tile * 128 + r;
       int row = -1, d = 0, foff = 0, utt = 0, ph = 0;
       if (sidx < p.n_rows) {
@@ -243,54 +270,59 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
         }
 
         // ---------------- L0, L1: zoneout LSTM cells
+        // Work item = 4 hidden units (16 accumulator columns) of this thread's row. The global operands of item
+        // i+1 (hoisted gate term, old cell state, old z) are requested BEFORE item i is computed -- and before
+        // waiting for the next accumulator buffer -- so their latency hides behind the MMAs.
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
           const uint8_t* zcur = layer == 0 ? z0cur : z1cur;
           uint8_t* znew = layer == 0 ? z0new : z1new;
           float* cl = cws + (size_t)layer * H * 128;
+          const int items = gate_chunks * 8;                         // 8 items of 4 units per 256-column chunk half
+          GatePref cur, nxt;
+          gate_prefetch(cur, layer, hsel * 32, r, m, g0t, p.b1, cl, zcur);
 #pragma unroll 1
-          for (int c = 0; c < gate_chunks; ++c) {
-            const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
-            mbar_wait(&sh.tmem_full[buf], use & 1u);
-            tc_fence_after();
-#pragma unroll 1
-            for (int g = 0; g < 4; ++g) {
-              float v[32];
-              tmem_ld32(lane_addr + buf * 256u + (uint32_t)(hsel * 128 + g * 32), v);
-              const int u0 = c * 64 + hsel * 32 + g * 8;           // first of 8 hidden units
-              const uint4 zraw = *reinterpret_cast<const uint4*>(zcur + ((size_t)(u0 >> 3) * 128 + r) * 16);
-              const uint32_t zr[4] = {zraw.x, zraw.y, zraw.z, zraw.w};
-              float zn[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int u = u0 + j;
-                float4 add;
-                if (layer == 0) {
-                  add = __ldg(reinterpret_cast<const float4*>(g0t + ((size_t)u * 128 + r) * 4));
-                  const float4 wp = __ldg(reinterpret_cast<const float4*>(p.wpos + 4 * u));
-                  add.x = fmaf(pos, wp.x, add.x); add.y = fmaf(pos, wp.y, add.y);
-                  add.z = fmaf(pos, wp.z, add.z); add.w = fmaf(pos, wp.w, add.w);
-                } else {
-                  add = __ldg(reinterpret_cast<const float4*>(p.b1 + 4 * u));
-                }
-                const float ig = sigmoid_fast(v[4 * j] + add.x), fg = sigmoid_fast(v[4 * j + 1] + add.y);
-                const float gg = tanh_fast(v[4 * j + 2] + add.z), og = sigmoid_fast(v[4 * j + 3] + add.w);
-                const float cold = m == 0 ? 0.f : cl[(size_t)u * 128 + r];
-                const float cn = fmaf(fg, cold, ig * gg);
-                const float hn = og * tanh_fast(cn);
-                const uint32_t zw = zr[j >> 1];
-                const float zold = __uint_as_float((j & 1) ? (zw & 0xFFFF0000u) : (zw << 16));
-                zn[j] = fmaf(zo, zold, zk * hn);                    // decoder_sa.py:95-96 (eval blend)
-                cl[(size_t)u * 128 + r] = fmaf(zo, cold, zk * cn);
-              }
-              uint4 w;
-              w.x = pack_bf16(zn[0], zn[1]); w.y = pack_bf16(zn[2], zn[3]);
-              w.z = pack_bf16(zn[4], zn[5]); w.w = pack_bf16(zn[6], zn[7]);
-              *reinterpret_cast<uint4*>(znew + ((size_t)(u0 >> 3) * 128 + r) * 16) = w;
+          for (int it = 0; it < items; ++it) {
+            const int c = it >> 3, g = it & 7;
+            const int u0 = c * 64 + hsel * 32 + g * 4;               // first of 4 hidden units
+            if (it + 1 < items) {
+              const int c2 = (it + 1) >> 3, g2 = (it + 1) & 7;
+              gate_prefetch(nxt, layer, c2 * 64 + hsel * 32 + g2 * 4, r, m, g0t, p.b1, cl, zcur);
             }
-            tc_fence_before();
-            mbar_arrive(&sh.tmem_empty[buf]);
-            ++chunk_ctr;
+            const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
+            if (g == 0) {
+              mbar_wait(&sh.tmem_full[buf], use & 1u);
+              tc_fence_after();
+            }
+            float v[16];
+            tmem_ld16(lane_addr + buf * 256u + (uint32_t)(hsel * 128 + g * 16), v);
+            float zn[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 add = cur.add[j];
+              if (layer == 0) {
+                const float4 wp = __ldg(reinterpret_cast<const float4*>(p.wpos + 4 * (u0 + j)));
+                add.x = fmaf(pos, wp.x, add.x); add.y = fmaf(pos, wp.y, add.y);
+                add.z = fmaf(pos, wp.z, add.z); add.w = fmaf(pos, wp.w, add.w);
+              }
+              const float ig = sigmoid_fast(v[4 * j] + add.x), fg = sigmoid_fast(v[4 * j + 1] + add.y);
+              const float gg = tanh_fast(v[4 * j + 2] + add.z), og = sigmoid_fast(v[4 * j + 3] + add.w);
+              const float cold = cur.cold[j];
+              const float cn = fmaf(fg, cold, ig * gg);
+              const float hn = og * tanh_fast(cn);
+              const uint32_t zw = j < 2 ? cur.z.x : cur.z.y;
+              const float zold = __uint_as_float((j & 1) ? (zw & 0xFFFF0000u) : (zw << 16));
+              zn[j] = fmaf(zo, zold, zk * hn);                       // decoder_sa.py:95-96 (eval blend)
+              cl[(size_t)(u0 + j) * 128 + r] = fmaf(zo, cold, zk * cn);
+            }
+            *reinterpret_cast<uint2*>(znew + ((size_t)(u0 >> 3) * 128 + r) * 16 + (u0 & 4) * 2) =
+                make_uint2(pack_bf16(zn[0], zn[1]), pack_bf16(zn[2], zn[3]));
+            if (g == 7) {
+              tc_fence_before();
+              mbar_arrive(&sh.tmem_empty[buf]);
+              ++chunk_ctr;
+            }
+            cur = nxt;
           }
           fence_proxy_async_all();
           mbar_arrive(&sh.a_ready[3 + layer]);
@@ -299,16 +331,28 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
         // ---------------- F: feat_out (+ hoisted h term) -> output frame (ragged store) and x0 image
         {
           const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
+          // 16-column groups: warps with hsel == 0 take groups 0,2,4.., hsel == 1 take 1,3,..
+          // hoisted h-term of this thread's groups: requested before waiting for the accumulator
+          float4 y0[4][4];                                           // up to 4 groups (odim <= 128)
+#pragma unroll
+          for (int gi = 0; gi < 4; ++gi) {
+            const int g = hsel + 2 * gi;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd)
+              y0[gi][qd] = g < O / 16 ? __ldg(reinterpret_cast<const float4*>(y0t + ((size_t)(g * 4 + qd) * 128 + r) * 4))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           mbar_wait(&sh.tmem_full[buf], use & 1u);
           tc_fence_after();
-          // 16-column groups: warps with hsel == 0 take groups 0,2,4.., hsel == 1 take 1,3,..
-          for (int g = hsel; g < O / 16; g += 2) {
+#pragma unroll
+          for (int gi = 0; gi < 4; ++gi) {
+            const int g = hsel + 2 * gi;
+            if (g >= O / 16) break;
             float v[16];
             tmem_ld16(lane_addr + buf * 256u + (uint32_t)(g * 16), v);
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) {
-              const float4 y0 = __ldg(reinterpret_cast<const float4*>(y0t + ((size_t)(g * 4 + qd) * 128 + r) * 4));
-              v[4 * qd] += y0.x; v[4 * qd + 1] += y0.y; v[4 * qd + 2] += y0.z; v[4 * qd + 3] += y0.w;
+              v[4 * qd] += y0[gi][qd].x; v[4 * qd + 1] += y0[gi][qd].y; v[4 * qd + 2] += y0[gi][qd].z; v[4 * qd + 3] += y0[gi][qd].w;
             }
             if (row >= 0 && m < d) {                               // exhausted rows are masked (decoder_sa.py:625-629)
               float4* o = reinterpret_cast<float4*>(p.before + ((size_t)foff + m) * O + g * 16);
