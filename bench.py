@@ -138,7 +138,7 @@ def config_dict(args, world):
     return {"workload": f"FCL-taco2-{args.model} batched inference, batch {args.batch} synthetic LJSpeech-shaped "
                         f"utterances per GPU" + (" (500-phoneme stress)" if args.stress else ""),
             "model_size": args.model, "per_gpu_batch": args.batch, "global_batch": args.batch * world,
-            "precision": args.precision, "prenet_dropout": 0.5, "forced_durations": True,
+            "precision": args.precision, "prenet_dropout": args.dropout, "forced_durations": True,
             "parallelism": f"utterance-sharded x{world}, no hot-path collective, final mel gather to rank 0",
             "l2": "flushed between timed steps (256 MiB write, outside the per-step events)"}
 
@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--latency-utts", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.5, help="prenet dropout rate (reference default 0.5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -176,7 +177,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     m = M.from_preset(args.model, seed=args.seed, device=dev, precision=args.precision)
-    m.set_prenet_dropout(rate=0.5, seed=1)
+    m.set_prenet_dropout(rate=args.dropout, seed=1)
     eng = m.engine()
     xs, ds = workload(args, rank)
     pl = planmod.make_plan(xs, ds)
@@ -195,7 +196,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         eng.stage_events = [] if timed else None
         e0.record()
-        res = eng.run_uploaded(pl, dinp, m.hp.zoneout_rate, 0.5, 1)
+        res = eng.run_uploaded(pl, dinp, m.hp.zoneout_rate, args.dropout, 1)
         gathered = fdist.gather_mels(res.out) if world > 1 else None
         e1.record()
         return e0, e1, res, eng.stage_events, gathered

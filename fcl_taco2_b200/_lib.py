@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -65,15 +65,19 @@ class DecoderParams(C.Structure):
 
 
 class DecoderBf16Params(C.Structure):
-    _fields_ = [("n_rows", i32), ("n_tiles", i32), ("n_slots", i32), ("dunits", i32), ("prenet_units", i32),
-                ("odim", i32), ("order", ptr), ("dur", ptr), ("frame_off", ptr), ("row_utt", ptr), ("row_phone", ptr),
-                ("g0h_t", ptr), ("y0h_t", ptr), ("w_stream", ptr), ("bp0", ptr), ("bp1", ptr), ("wpos", ptr),
-                ("b1", ptr), ("act_ws", ptr), ("c_ws", ptr), ("before", ptr), ("zoneout", f32), ("dropout_p", f32),
-                ("dropout_seed", u64)]
+    _fields_ = [("n_rows", i32), ("n_tiles", i32), ("n_slots", i32), ("eunits", i32), ("dunits", i32),
+                ("prenet_units", i32), ("odim", i32), ("order", ptr), ("dur", ptr), ("frame_off", ptr),
+                ("row_utt", ptr), ("row_phone", ptr), ("hn_img", ptr), ("w_stream", ptr), ("bp0", ptr), ("bp1", ptr),
+                ("wpos", ptr), ("b0", ptr), ("b1", ptr), ("act_ws", ptr), ("c_ws", ptr), ("before", ptr),
+                ("zoneout", f32), ("dropout_p", f32), ("dropout_seed", u64), ("trace", ptr), ("trace_cap", i32)]
+
+
+class PackRowsParams(C.Structure):
+    _fields_ = [("n_rows", i32), ("cols", i32), ("src", ptr), ("ld", i32), ("order", ptr), ("dst", ptr)]
 
 
 STRUCTS = [LenRegParams, FrameMapParams, ConvGemmParams, LayerNormParams, EmbedAddParams, BiLstmParams,
-           DecoderParams, ConvGemmBf16Params, DecoderBf16Params]
+           DecoderParams, ConvGemmBf16Params, DecoderBf16Params, PackRowsParams]
 
 ENTRY_POINTS = {
     "fcl_len_reg_scan": LenRegParams,
@@ -85,6 +89,7 @@ ENTRY_POINTS = {
     "fcl_decoder_f32": DecoderParams,
     "fcl_conv_gemm_bf16": ConvGemmBf16Params,
     "fcl_decoder_bf16": DecoderBf16Params,
+    "fcl_pack_rows_bf16": PackRowsParams,
 }
 PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_last_error", "fcl_sm_count", "fcl_struct_size",
                  "fcl_decoder_bf16_workspace"]

@@ -45,6 +45,7 @@ extern "C" int fcl_struct_size(int which) {
     case 6: return (int)sizeof(FclDecoderParams);
     case 7: return (int)sizeof(FclConvGemmBf16Params);
     case 8: return (int)sizeof(FclDecoderBf16Params);
+    case 9: return (int)sizeof(FclPackRowsParams);
     default: return -1;
   }
 }

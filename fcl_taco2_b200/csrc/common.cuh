@@ -35,18 +35,18 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
   return Philox4{c0, c1, c2, c3};
 }
 
-// keep decisions of prenet units 4*quad .. 4*quad+3 for (utt, phoneme, step, layer)
+// keep decisions of prenet units 8*oct .. 8*oct+7 for (utt, phoneme, step, layer): unit 8*oct+j uses the
+// 16-bit lane  (j & 1) ? word[j >> 1] >> 16 : word[j >> 1] & 0xffff  and is kept iff lane >= dropout_threshold16(p)
 __device__ __forceinline__ Philox4 dropout_words(uint64_t seed, uint32_t utt, uint32_t phoneme,
-                                                  uint32_t step, uint32_t layer, uint32_t quad) {
-  return philox4x32_10(quad, (step & 0xFFFFFFu) | (layer << 24), phoneme, utt,
+                                                  uint32_t step, uint32_t layer, uint32_t oct) {
+  return philox4x32_10(oct, (step & 0xFFFFFFu) | (layer << 24), phoneme, utt,
                        (uint32_t)(seed & 0xFFFFFFFFull), (uint32_t)(seed >> 32));
 }
 
-__host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
-  double t = (double)p * 4294967296.0;
-  t = t + 0.5;                       // round half up == Python round() except exact .5 ties (p is a config constant)
-  if (t >= 4294967295.0) return 4294967295u;
-  if (t <= 0.0) return 0u;
+__host__ __device__ __forceinline__ uint32_t dropout_threshold16(float p) {
+  float t = p * 65536.0f + 0.5f;
+  if (t >= 65535.0f) return 65535u;
+  if (t <= 0.0f) return 0u;
   return (uint32_t)t;
 }
 

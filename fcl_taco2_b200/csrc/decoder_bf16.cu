@@ -5,30 +5,33 @@
 // One CTA owns a tile of 128 duration-sorted phoneme rows for all of their steps (rows are independent, so
 // no inter-CTA communication exists). Per step it runs five dependent GEMM phases on the tensor cores
 //   P0 prenet.0 [128 x 80(->128)] x [256]      P1 prenet.1 [128 x 256] x [256]
-//   L0 gates of cell 0: [x2 | z0] (K = 256 + H) x 4H      L1 gates of cell 1: [z0' | z1] (K = 2H) x 4H
-//   F  feat_out: z1' (K = H) x 80
+//   L0 gates of cell 0: [x2 | h | z0] (K = 256 + E + H) x 4H     L1 gates of cell 1: [z0' | z1] (K = 2H) x 4H
+//   F  feat_out: [z1' | h] (K = H + E) x 80
 // with bf16 operands, fp32 accumulators in TMEM (two 256-column buffers: the epilogue of chunk j overlaps
-// the MMAs of chunk j+1), fp32 cell state. Weights (bf16, pre-tiled as UMMA core matrices, in consumption
-// order) and the activation operands stream through a 4-stage shared-memory ring with cp.async.bulk;
-// the activation operands of a tile (x0,x1,x2,z0,z1 as bf16 core-matrix images) live in a per-CTA global
-// scratch that stays L2-resident, written by the epilogue warps and re-read by the bulk copies
-// (generic->async proxy fence + mbarrier hand-over).
+// the MMAs of chunk j+1), fp32 cell state. The encoder state h of the tile is a K-slice of the A operand
+// (it is NOT hoisted into a per-row fp32 table: re-reading such a table every step made the epilogue
+// latency-bound on HBM). Weights (bf16, pre-tiled as UMMA core matrices, in consumption order) and the
+// activation operands stream through a 4-stage shared-memory ring with cp.async.bulk; the activation
+// operands of a tile (x0,x1,x2,z0,z1 as bf16 core-matrix images) live in a per-CTA global scratch that stays
+// L2-resident, written by the epilogue warps and re-read by the bulk copies (generic->async proxy fence +
+// mbarrier hand-over).
 //
-// Warp roles (384 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-11 = epilogue (TMEM lane quarter = warp % 4; warps 4-7 take the low half of a chunk's columns,
-// warps 8-11 the high half). Gate columns are interleaved (unit*4 + {i,f,g,o}) so one thread owns whole cells.
+// Warp roles (640 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-19 = epilogue (TMEM lane quarter = warp % 4; column quarter = (warp - 4) / 4: 64 of a chunk's 256
+// columns). Gate columns are interleaved (unit*4 + {i,f,g,o}) so one thread owns whole LSTM cells; the old
+// cell state / old z of the NEXT chunk are requested before the current chunk is computed.
 #include "common.cuh"
 #include "umma.cuh"
 
 namespace fcl {
 using namespace umma;
 
-constexpr int kDbThreads = 384;
+constexpr int kDbThreads = 640;
 constexpr int kDbStages = 4;
 constexpr uint32_t kABytes = 128u * 64u * 2u;           // one A stage: 128 rows x 64 k (bf16)
 constexpr uint32_t kBBytesMax = 256u * 64u * 2u;        // one B stage: up to 256 cols x 64 k
 constexpr uint32_t kStageBytes = kABytes + kBBytesMax;  // 48 KB
-constexpr int kEpiThreads = 256;
+constexpr int kEpiThreads = 512;
 
 struct DbShared {
   uint64_t full[kDbStages], empty[kDbStages];
@@ -56,22 +59,17 @@ __device__ __forceinline__ int db_tile(int tk, int n_tiles) {
   return t < n_tiles ? t : -2;          // -2: no tile for this CTA in the last, partial round
 }
 
-// global operands of one gate work item (4 hidden units of one row)
-struct GatePref {
-  float4 add[4];      // hoisted gate pre-activation (cell 0) or bias (cell 1), gates i,f,g,o
-  float cold[4];      // previous cell state
-  uint2 z;            // previous zoned-out hidden state, 4 x bf16
-};
-
-__device__ __forceinline__ void gate_prefetch(GatePref& pf, int layer, int u0, int r, int m, const float* __restrict__ g0t,
-                                              const float* __restrict__ b1, const float* cl, const uint8_t* zcur) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    pf.add[j] = layer == 0 ? __ldg(reinterpret_cast<const float4*>(g0t + ((size_t)(u0 + j) * 128 + r) * 4))
-                           : __ldg(reinterpret_cast<const float4*>(b1 + 4 * (u0 + j)));
-    pf.cold[j] = m == 0 ? 0.f : __ldcg(cl + (size_t)(u0 + j) * 128 + r);
+// optional timeline trace of CTA 0 (debug/profiling aid; p.trace == nullptr in production).
+// record = {event id, clock64}; ids: 100+phase*10+chunk (MMA: accumulator free), 200+.. (MMA: first stage landed),
+// 300+.. (MMA: chunk issued), 400+.. (epilogue: accumulator ready), 500+.. (epilogue: chunk done), 600+phase (producer: operand ready)
+__device__ __forceinline__ void db_trace(const FclDecoderBf16Params& p, int id) {
+  if (p.trace && blockIdx.x == 0) {
+    const unsigned long long n = atomicAdd(reinterpret_cast<unsigned long long*>(p.trace), 1ull);
+    if (n < (unsigned long long)p.trace_cap) {
+      p.trace[2 + 2 * n] = id;
+      p.trace[3 + 2 * n] = clock64();
+    }
   }
-  pf.z = __ldcg(reinterpret_cast<const uint2*>(zcur + ((size_t)(u0 >> 3) * 128 + r) * 16 + (u0 & 4) * 2));
 }
 
 __global__ void __launch_bounds__(kDbThreads, 1)
@@ -81,7 +79,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.dunits, U = p.prenet_units, O = p.odim;
   const int H4 = 4 * H;
-  const int kU = U / 64, kH = H / 64;               // K stages of the prenet / hidden operands
+  const int kU = U / 64, kH = H / 64, kE = p.eunits / 64;   // K stages of the prenet / hidden / encoder-state operands
   const int gate_chunks = H4 / 256;
   uint8_t* act = reinterpret_cast<uint8_t*>(p.act_ws) + (size_t)blockIdx.x * db_act_bytes(U, H);
   float* cws = p.c_ws + (size_t)blockIdx.x * 2 * H * 128;
@@ -108,6 +106,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
       uint32_t rdy[5] = {0, 0, 0, 0, 0};              // parity of each a_ready barrier
       for (int tk = 0, tile; (tile = db_tile(tk, p.n_tiles)) >= 0; ++tk) {
         const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
+        const uint8_t* himg = reinterpret_cast<const uint8_t*>(p.hn_img) + (size_t)tile * p.eunits * 128 * 2;
         for (int m = 0; m < steps; ++m) {
           const int zp = m & 1;
           const uint8_t* z0cur = act + db_z_off(U, H, zp), *z0new = act + db_z_off(U, H, zp ^ 1);
@@ -116,17 +115,20 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
           for (int phase = 0; phase < 5; ++phase) {
             mbar_wait(&sh.a_ready[phase], rdy[phase]);
             rdy[phase] ^= 1u;
+            db_trace(p, 600 + phase);
             const int nchunks = (phase == 2 || phase == 3) ? gate_chunks : 1;
-            const int kst = phase == 0 ? 2 : phase == 1 ? kU : phase == 2 ? kU + kH : phase == 3 ? 2 * kH : kH;
+            const int kst = phase == 0 ? 2 : phase == 1 ? kU : phase == 2 ? kU + kE + kH : phase == 3 ? 2 * kH : kH + kE;
             const uint32_t bb = phase == 4 ? b_bytes_feat : b_bytes_wide;
             for (int c = 0; c < nchunks; ++c) {
               for (int ks = 0; ks < kst; ++ks) {
                 const uint8_t* asrc;
                 if (phase == 0) asrc = act + db_x0_off() + (size_t)ks * kABytes;
                 else if (phase == 1) asrc = act + db_x1_off() + (size_t)ks * kABytes;
-                else if (phase == 2) asrc = ks < kU ? act + db_x2_off(U) + (size_t)ks * kABytes : z0cur + (size_t)(ks - kU) * kABytes;
+                else if (phase == 2) asrc = ks < kU ? act + db_x2_off(U) + (size_t)ks * kABytes
+                                          : ks < kU + kE ? himg + (size_t)(ks - kU) * kABytes
+                                                         : z0cur + (size_t)(ks - kU - kE) * kABytes;
                 else if (phase == 3) asrc = ks < kH ? z0new + (size_t)ks * kABytes : z1cur + (size_t)(ks - kH) * kABytes;
-                else asrc = z1new + (size_t)ks * kABytes;
+                else asrc = ks < kH ? z1new + (size_t)ks * kABytes : himg + (size_t)(ks - kH) * kABytes;
                 mbar_wait(&sh.empty[stage], sphase ^ 1u);
                 mbar_arrive_expect_tx(&sh.full[stage], kABytes + bb);
                 uint8_t* st = smem + (size_t)stage * kStageBytes;
@@ -152,7 +154,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
         for (int m = 0; m < steps; ++m) {
           for (int phase = 0; phase < 5; ++phase) {
             const int nchunks = (phase == 2 || phase == 3) ? gate_chunks : 1;
-            const int kst = phase == 0 ? 2 : phase == 1 ? kU : phase == 2 ? kU + kH : phase == 3 ? 2 * kH : kH;
+            const int kst = phase == 0 ? 2 : phase == 1 ? kU : phase == 2 ? kU + kE + kH : phase == 3 ? 2 * kH : kH + kE;
             const uint32_t ncols = phase == 4 ? (uint32_t)O : 256u;
             const uint32_t idesc = phase == 4 ? idesc_feat : idesc_wide;
             const uint32_t b_lbo = ncols * 16u;
@@ -160,10 +162,12 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
               const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
               mbar_wait(&sh.tmem_empty[buf], (use & 1u) ^ 1u);
               tc_fence_after();
+              db_trace(p, 100 + phase * 10 + c);
               const uint32_t d_tmem = tmem + buf * 256u;
               for (int ks = 0; ks < kst; ++ks) {
                 mbar_wait(&sh.full[stage], sphase);
                 tc_fence_after();
+                if (ks == 0) db_trace(p, 200 + phase * 10 + c);
                 const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes);
                 const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
@@ -176,6 +180,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
                 if (++stage == kDbStages) { stage = 0; sphase ^= 1u; }
               }
               mma_commit(&sh.tmem_full[buf]);
+              db_trace(p, 300 + phase * 10 + c);
               ++chunk_ctr;
             }
           }
@@ -184,14 +189,14 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ================================================================ epilogue (256 threads)
-    const int q = warp & 3, hsel = (warp - 4) >> 2;
+    // ================================================================ epilogue (512 threads)
+    const int q = warp & 3, cs = (warp - 4) >> 2;      // TMEM lane quarter, column quarter
     const int r = q * 32 + lane;                       // row within the tile == TMEM lane
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t chunk_ctr = 0;
     const float zo = p.zoneout, zk = 1.0f - p.zoneout;
     const bool use_drop = p.dropout_p > 0.f;
-    const uint32_t drop_thr = dropout_threshold(p.dropout_p);
+    const uint32_t drop_thr = dropout_threshold16(p.dropout_p);
     const float drop_scale = use_drop ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
 
     for (int tk = 0, tile; (tile = db_tile(tk, p.n_tiles)) >= 0; ++tk) {
@@ -206,19 +211,17 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
       }
       const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
       if (steps == 0) continue;
-      // ---- tile init: zero x0 (all 16 k-chunks) and the "current" z images; this thread's half of the chunks
+      // ---- tile init: zero x0 (all 16 k-chunks) and the "current" z images; this thread's quarter of the chunks
       {
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-        for (int kc = hsel; kc < 16; kc += 2) *reinterpret_cast<uint4*>(act + db_x0_off() + ((size_t)kc * 128 + r) * 16) = z4;
-        for (int kc = hsel; kc < H / 8; kc += 2) {
+        for (int kc = cs; kc < 16; kc += 4) *reinterpret_cast<uint4*>(act + db_x0_off() + ((size_t)kc * 128 + r) * 16) = z4;
+        for (int kc = cs; kc < H / 8; kc += 4) {
           *reinterpret_cast<uint4*>(act + db_z_off(U, H, 0) + ((size_t)kc * 128 + r) * 16) = z4;
           *reinterpret_cast<uint4*>(act + db_z_off(U, H, 2) + ((size_t)kc * 128 + r) * 16) = z4;
         }
         fence_proxy_async_all();
         mbar_arrive(&sh.a_ready[0]);
       }
-      const float* g0t = p.g0h_t + (size_t)tile * H4 * 128;     // [H][128][4] fp32
-      const float* y0t = p.y0h_t + (size_t)tile * O * 128;      // [O/4][128][4]
 
       for (int m = 0; m < steps; ++m) {
         const int zp = m & 1;
@@ -226,40 +229,41 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
         uint8_t* z1cur = act + db_z_off(U, H, 2 + zp), *z1new = act + db_z_off(U, H, 2 + (zp ^ 1));
         const float pos = (row >= 0 && m < d) ? __fdiv_rn((float)m, (float)d) : 0.f;
 
-        // ---------------- P0, P1: prenet layers (bias, ReLU, dropout) -> x1 / x2 images
+        // ---------------- P0, P1: prenet layers (bias, ReLU, dropout) -> x1 / x2 images; 64 columns per thread
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
           const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
           mbar_wait(&sh.tmem_full[buf], use & 1u);
           tc_fence_after();
+          if (tid == 128) db_trace(p, 400 + layer * 10);
           const float* bias = layer == 0 ? p.bp0 : p.bp1;
           uint8_t* dst = act + (layer == 0 ? db_x1_off() : db_x2_off(U));
 #pragma unroll 1
           for (int g = 0; g < 4; ++g) {
-            float v[32];
-            const int col0 = hsel * 128 + g * 32;
-            tmem_ld32(lane_addr + buf * 256u + (uint32_t)col0, v);
+            float v[16];
+            const int col0 = cs * 64 + g * 16;
+            tmem_ld16(lane_addr + buf * 256u + (uint32_t)col0, v);
 #pragma unroll
-            for (int qd = 0; qd < 8; ++qd) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0) + qd);
-              float x[4] = {fmaxf(v[4 * qd] + b4.x, 0.f), fmaxf(v[4 * qd + 1] + b4.y, 0.f),
-                            fmaxf(v[4 * qd + 2] + b4.z, 0.f), fmaxf(v[4 * qd + 3] + b4.w, 0.f)};
-              if (use_drop) {
-                const Philox4 rnd = dropout_words(p.dropout_seed, (uint32_t)utt, (uint32_t)ph, (uint32_t)m,
-                                                  (uint32_t)layer, (uint32_t)((col0 >> 2) + qd));
-                x[0] = rnd.x >= drop_thr ? x[0] * drop_scale : 0.f;
-                x[1] = rnd.y >= drop_thr ? x[1] * drop_scale : 0.f;
-                x[2] = rnd.z >= drop_thr ? x[2] * drop_scale : 0.f;
-                x[3] = rnd.w >= drop_thr ? x[3] * drop_scale : 0.f;
+            for (int h8 = 0; h8 < 2; ++h8) {                         // 8 columns share one Philox call
+              Philox4 rnd = Philox4{0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+              if (use_drop)
+                rnd = dropout_words(p.dropout_seed, (uint32_t)utt, (uint32_t)ph, (uint32_t)m, (uint32_t)layer,
+                                    (uint32_t)((col0 >> 3) + h8));
+              const uint32_t wv[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+              const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * h8));
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * h8) + 1);
+              const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+              float x[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t u16 = (j & 1) ? (wv[j >> 1] >> 16) : (wv[j >> 1] & 0xFFFFu);
+                const float y = fmaxf(v[8 * h8 + j] + bv[j], 0.f) * drop_scale;
+                x[j] = u16 >= drop_thr ? y : 0.f;
               }
-              v[4 * qd] = x[0]; v[4 * qd + 1] = x[1]; v[4 * qd + 2] = x[2]; v[4 * qd + 3] = x[3];
-            }
-#pragma unroll
-            for (int k8 = 0; k8 < 4; ++k8) {
               uint4 w;
-              w.x = pack_bf16(v[8 * k8], v[8 * k8 + 1]); w.y = pack_bf16(v[8 * k8 + 2], v[8 * k8 + 3]);
-              w.z = pack_bf16(v[8 * k8 + 4], v[8 * k8 + 5]); w.w = pack_bf16(v[8 * k8 + 6], v[8 * k8 + 7]);
-              *reinterpret_cast<uint4*>(dst + ((size_t)((col0 >> 3) + k8) * 128 + r) * 16) = w;
+              w.x = pack_bf16(x[0], x[1]); w.y = pack_bf16(x[2], x[3]);
+              w.z = pack_bf16(x[4], x[5]); w.w = pack_bf16(x[6], x[7]);
+              *reinterpret_cast<uint4*>(dst + ((size_t)((col0 >> 3) + h8) * 128 + r) * 16) = w;
             }
           }
           tc_fence_before();
@@ -267,93 +271,93 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
           ++chunk_ctr;
           fence_proxy_async_all();
           mbar_arrive(&sh.a_ready[1 + layer]);
+          if (tid == 128) db_trace(p, 500 + layer * 10);
         }
 
-        // ---------------- L0, L1: zoneout LSTM cells
-        // Work item = 4 hidden units (16 accumulator columns) of this thread's row. The global operands of item
-        // i+1 (hoisted gate term, old cell state, old z) are requested BEFORE item i is computed -- and before
-        // waiting for the next accumulator buffer -- so their latency hides behind the MMAs.
+        // ---------------- L0, L1: zoneout LSTM cells; per chunk this thread owns 16 hidden units of its row.
+        // The old cell state (fp32) and old z (bf16) of chunk c+1 are requested before chunk c is computed, and
+        // those of chunk 0 before waiting for its accumulator: their L2 latency hides behind the MMAs.
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
           const uint8_t* zcur = layer == 0 ? z0cur : z1cur;
           uint8_t* znew = layer == 0 ? z0new : z1new;
           float* cl = cws + (size_t)layer * H * 128;
-          const int items = gate_chunks * 8;                         // 8 items of 4 units per 256-column chunk half
-          GatePref cur, nxt;
-          gate_prefetch(cur, layer, hsel * 32, r, m, g0t, p.b1, cl, zcur);
+          const float* bias = layer == 0 ? p.b0 : p.b1;
+          float c_cur[16], c_nxt[16];
+          uint4 z_cur[2], z_nxt[2];
+          {
+            const int u0 = cs * 16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) c_cur[j] = m == 0 ? 0.f : __ldcg(cl + (size_t)(u0 + j) * 128 + r);
+            z_cur[0] = __ldcg(reinterpret_cast<const uint4*>(zcur + ((size_t)(u0 >> 3) * 128 + r) * 16));
+            z_cur[1] = __ldcg(reinterpret_cast<const uint4*>(zcur + ((size_t)((u0 >> 3) + 1) * 128 + r) * 16));
+          }
 #pragma unroll 1
-          for (int it = 0; it < items; ++it) {
-            const int c = it >> 3, g = it & 7;
-            const int u0 = c * 64 + hsel * 32 + g * 4;               // first of 4 hidden units
-            if (it + 1 < items) {
-              const int c2 = (it + 1) >> 3, g2 = (it + 1) & 7;
-              gate_prefetch(nxt, layer, c2 * 64 + hsel * 32 + g2 * 4, r, m, g0t, p.b1, cl, zcur);
+          for (int c = 0; c < gate_chunks; ++c) {
+            const int u0 = c * 64 + cs * 16;                          // first of this thread's 16 hidden units
+            if (c + 1 < gate_chunks) {
+              const int un = u0 + 64;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) c_nxt[j] = m == 0 ? 0.f : __ldcg(cl + (size_t)(un + j) * 128 + r);
+              z_nxt[0] = __ldcg(reinterpret_cast<const uint4*>(zcur + ((size_t)(un >> 3) * 128 + r) * 16));
+              z_nxt[1] = __ldcg(reinterpret_cast<const uint4*>(zcur + ((size_t)((un >> 3) + 1) * 128 + r) * 16));
             }
             const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
-            if (g == 0) {
-              mbar_wait(&sh.tmem_full[buf], use & 1u);
-              tc_fence_after();
-            }
-            float v[16];
-            tmem_ld16(lane_addr + buf * 256u + (uint32_t)(hsel * 128 + g * 16), v);
-            float zn[4];
+            mbar_wait(&sh.tmem_full[buf], use & 1u);
+            tc_fence_after();
+            if (tid == 128) db_trace(p, 400 + (2 + layer) * 10 + c);
+            uint32_t zout[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 add = cur.add[j];
-              if (layer == 0) {
-                const float4 wp = __ldg(reinterpret_cast<const float4*>(p.wpos + 4 * (u0 + j)));
-                add.x = fmaf(pos, wp.x, add.x); add.y = fmaf(pos, wp.y, add.y);
-                add.z = fmaf(pos, wp.z, add.z); add.w = fmaf(pos, wp.w, add.w);
+            for (int g = 0; g < 4; ++g) {                             // 4 units (16 accumulator columns) at a time
+              float v[16];
+              tmem_ld16(lane_addr + buf * 256u + (uint32_t)(cs * 64 + g * 16), v);
+              float zn[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int ul = g * 4 + j, u = u0 + ul;
+                float4 add = __ldg(reinterpret_cast<const float4*>(bias + 4 * u));
+                if (layer == 0) {
+                  const float4 wp = __ldg(reinterpret_cast<const float4*>(p.wpos + 4 * u));
+                  add.x = fmaf(pos, wp.x, add.x); add.y = fmaf(pos, wp.y, add.y);
+                  add.z = fmaf(pos, wp.z, add.z); add.w = fmaf(pos, wp.w, add.w);
+                }
+                const float ig = sigmoid_fast(v[4 * j] + add.x), fg = sigmoid_fast(v[4 * j + 1] + add.y);
+                const float gg = tanh_fast(v[4 * j + 2] + add.z), og = sigmoid_fast(v[4 * j + 3] + add.w);
+                const float cold = c_cur[ul];
+                const float cn = fmaf(fg, cold, ig * gg);
+                const float hn = og * tanh_fast(cn);
+                const uint4 zq = z_cur[ul >> 3];
+                const uint32_t zw = ((ul >> 1) & 3) == 0 ? zq.x : ((ul >> 1) & 3) == 1 ? zq.y : ((ul >> 1) & 3) == 2 ? zq.z : zq.w;
+                const float zold = __uint_as_float((ul & 1) ? (zw & 0xFFFF0000u) : (zw << 16));
+                zn[j] = fmaf(zo, zold, zk * hn);                      // decoder_sa.py:95-96 (eval blend)
+                cl[(size_t)u * 128 + r] = fmaf(zo, cold, zk * cn);
               }
-              const float ig = sigmoid_fast(v[4 * j] + add.x), fg = sigmoid_fast(v[4 * j + 1] + add.y);
-              const float gg = tanh_fast(v[4 * j + 2] + add.z), og = sigmoid_fast(v[4 * j + 3] + add.w);
-              const float cold = cur.cold[j];
-              const float cn = fmaf(fg, cold, ig * gg);
-              const float hn = og * tanh_fast(cn);
-              const uint32_t zw = j < 2 ? cur.z.x : cur.z.y;
-              const float zold = __uint_as_float((j & 1) ? (zw & 0xFFFF0000u) : (zw << 16));
-              zn[j] = fmaf(zo, zold, zk * hn);                       // decoder_sa.py:95-96 (eval blend)
-              cl[(size_t)(u0 + j) * 128 + r] = fmaf(zo, cold, zk * cn);
+              zout[2 * g] = pack_bf16(zn[0], zn[1]);
+              zout[2 * g + 1] = pack_bf16(zn[2], zn[3]);
             }
-            *reinterpret_cast<uint2*>(znew + ((size_t)(u0 >> 3) * 128 + r) * 16 + (u0 & 4) * 2) =
-                make_uint2(pack_bf16(zn[0], zn[1]), pack_bf16(zn[2], zn[3]));
-            if (g == 7) {
-              tc_fence_before();
-              mbar_arrive(&sh.tmem_empty[buf]);
-              ++chunk_ctr;
-            }
-            cur = nxt;
+            tc_fence_before();
+            mbar_arrive(&sh.tmem_empty[buf]);
+            ++chunk_ctr;
+            *reinterpret_cast<uint4*>(znew + ((size_t)(u0 >> 3) * 128 + r) * 16) = make_uint4(zout[0], zout[1], zout[2], zout[3]);
+            *reinterpret_cast<uint4*>(znew + ((size_t)((u0 >> 3) + 1) * 128 + r) * 16) = make_uint4(zout[4], zout[5], zout[6], zout[7]);
+            if (tid == 128) db_trace(p, 500 + (2 + layer) * 10 + c);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) c_cur[j] = c_nxt[j];
+            z_cur[0] = z_nxt[0]; z_cur[1] = z_nxt[1];
           }
           fence_proxy_async_all();
           mbar_arrive(&sh.a_ready[3 + layer]);
         }
 
-        // ---------------- F: feat_out (+ hoisted h term) -> output frame (ragged store) and x0 image
+        // ---------------- F: feat_out -> output frame (ragged store) and x0 image; 16-column groups, group g -> warp set g % 4
         {
           const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
-          // 16-column groups: warps with hsel == 0 take groups 0,2,4.., hsel == 1 take 1,3,..
-          // hoisted h-term of this thread's groups: requested before waiting for the accumulator
-          float4 y0[4][4];                                           // up to 4 groups (odim <= 128)
-#pragma unroll
-          for (int gi = 0; gi < 4; ++gi) {
-            const int g = hsel + 2 * gi;
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd)
-              y0[gi][qd] = g < O / 16 ? __ldg(reinterpret_cast<const float4*>(y0t + ((size_t)(g * 4 + qd) * 128 + r) * 4))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
           mbar_wait(&sh.tmem_full[buf], use & 1u);
           tc_fence_after();
-#pragma unroll
-          for (int gi = 0; gi < 4; ++gi) {
-            const int g = hsel + 2 * gi;
-            if (g >= O / 16) break;
+          if (tid == 128) db_trace(p, 440);
+          for (int g = cs; g < O / 16; g += 4) {
             float v[16];
             tmem_ld16(lane_addr + buf * 256u + (uint32_t)(g * 16), v);
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) {
-              v[4 * qd] += y0[gi][qd].x; v[4 * qd + 1] += y0[gi][qd].y; v[4 * qd + 2] += y0[gi][qd].z; v[4 * qd + 3] += y0[gi][qd].w;
-            }
             if (row >= 0 && m < d) {                               // exhausted rows are masked (decoder_sa.py:625-629)
               float4* o = reinterpret_cast<float4*>(p.before + ((size_t)foff + m) * O + g * 16);
 #pragma unroll
@@ -374,6 +378,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
             fence_proxy_async_all();
             mbar_arrive(&sh.a_ready[0]);
           }
+          if (tid == 128) db_trace(p, 540);
         }
       }
     }
@@ -395,9 +400,10 @@ extern "C" int fcl_decoder_bf16_workspace(int32_t prenet_units, int32_t dunits, 
 
 extern "C" int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream) {
   using namespace fcl;
-  FCL_REQUIRE(p && p->order && p->dur && p->frame_off && p->row_utt && p->row_phone && p->g0h_t && p->y0h_t &&
-                  p->w_stream && p->bp0 && p->bp1 && p->wpos && p->b1 && p->act_ws && p->c_ws && p->before,
+  FCL_REQUIRE(p && p->order && p->dur && p->frame_off && p->row_utt && p->row_phone && p->hn_img &&
+                  p->w_stream && p->bp0 && p->bp1 && p->wpos && p->b0 && p->b1 && p->act_ws && p->c_ws && p->before,
               "null pointer");
+  FCL_REQUIRE(p->eunits % 64 == 0 && p->eunits >= 64, "eunits must be a multiple of 64");
   FCL_REQUIRE(p->n_rows > 0 && p->n_tiles == (p->n_rows + 127) / 128, "n_tiles must be ceil(n_rows / 128)");
   FCL_REQUIRE(p->prenet_units == 256, "prenet_units must be 256 (one 256-column chunk)");
   FCL_REQUIRE(p->dunits % 64 == 0 && p->dunits >= 64, "dunits must be a multiple of 64");

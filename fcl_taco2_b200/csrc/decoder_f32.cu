@@ -88,7 +88,7 @@ decoder_f32_kernel(FclDecoderParams p) {
 
   const float zo = p.zoneout, zk = 1.0f - p.zoneout;
   const bool use_drop = p.dropout_p > 0.f;
-  const uint32_t drop_thr = dropout_threshold(p.dropout_p);
+  const uint32_t drop_thr = dropout_threshold16(p.dropout_p);
   const float drop_scale = use_drop ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
   const int H4 = 4 * H;
   constexpr int kMaxChunks = 4;                     // H / CT <= 4  (H <= 1024 with R=16, <= 512 with R=32)
@@ -116,11 +116,12 @@ decoder_f32_kernel(FclDecoderParams p) {
           for (int j = 0; j < 4; ++j) v[j] = fmaxf(acc[i][j], 0.f);
           if (use_drop) {
             const Philox4 rnd = dropout_words(p.dropout_seed, (uint32_t)m_utt[r0 + i], (uint32_t)m_ph[r0 + i],
-                                              (uint32_t)m, (uint32_t)layer, (uint32_t)(col >> 2));
-            v[0] = rnd.x >= drop_thr ? v[0] * drop_scale : 0.f;
-            v[1] = rnd.y >= drop_thr ? v[1] * drop_scale : 0.f;
-            v[2] = rnd.z >= drop_thr ? v[2] * drop_scale : 0.f;
-            v[3] = rnd.w >= drop_thr ? v[3] * drop_scale : 0.f;
+                                              (uint32_t)m, (uint32_t)layer, (uint32_t)(col >> 3));
+            const uint32_t wa = (col & 4) ? rnd.z : rnd.x, wb = (col & 4) ? rnd.w : rnd.y;   // lanes of units col..col+3
+            v[0] = (wa & 0xFFFFu) >= drop_thr ? v[0] * drop_scale : 0.f;
+            v[1] = (wa >> 16) >= drop_thr ? v[1] * drop_scale : 0.f;
+            v[2] = (wb & 0xFFFFu) >= drop_thr ? v[2] * drop_scale : 0.f;
+            v[3] = (wb >> 16) >= drop_thr ? v[3] * drop_scale : 0.f;
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) o_s[(col + j) * LD + r0 + i] = v[j];

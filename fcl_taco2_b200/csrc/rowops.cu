@@ -6,6 +6,7 @@
 //                       (e2e_tts_tacotron2_sa.py:435-443,657-658; decoder_sa.py:570-571).
 // HBM-bound: one warp per row, float4 accesses.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace fcl {
 
@@ -110,7 +111,43 @@ embed_add_kernel(FclEmbedAddParams p) {
   }
 }
 
+// gather rows by `order`, round to bf16, write the UMMA operand image [tile][cols/8][128][8]
+__global__ void __launch_bounds__(256)
+pack_rows_bf16_kernel(FclPackRowsParams p) {
+  const int c8 = p.cols >> 3;
+  const int tiles = (p.n_rows + 127) >> 7;
+  const size_t total = (size_t)tiles * c8 * 128;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i & 127);
+    const size_t tk = i >> 7;
+    const int kc = (int)(tk % c8), tile = (int)(tk / c8);
+    const int sidx = tile * 128 + r;
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (sidx < p.n_rows) {
+      const float4* src = reinterpret_cast<const float4*>(p.src + (size_t)p.order[sidx] * p.ld + kc * 8);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+      w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
+      w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+    }
+    reinterpret_cast<uint4*>(p.dst)[i] = w;
+  }
+}
+
 }  // namespace fcl
+
+extern "C" int fcl_pack_rows_bf16(const FclPackRowsParams* p, void* stream) {
+  using namespace fcl;
+  FCL_REQUIRE(p && p->src && p->order && p->dst, "null pointer");
+  FCL_REQUIRE(p->n_rows > 0 && p->cols % 8 == 0 && p->ld % 4 == 0, "bad sizes");
+  int sms = fcl_sm_count();
+  if (sms < 0) return sms;
+  const size_t total = (size_t)((p->n_rows + 127) / 128) * (p->cols / 8) * 128;
+  int blocks = (int)min((total + 255) / 256, (size_t)sms * 8);
+  pack_rows_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*p);
+  return check_launch("fcl_pack_rows_bf16");
+}
 
 extern "C" int fcl_layernorm_f32(const FclLayerNormParams* p, void* stream) {
   using namespace fcl;

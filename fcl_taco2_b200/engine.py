@@ -55,7 +55,7 @@ class Engine:
         if precision == "bf16":
             from . import pack as _pack
             self.wb = {k: (t.to(self.device), nt, ks) for k, (t, nt, ks) in _pack.pack_bf16(packed).items()
-                       if bf16_gemms is None or k in bf16_gemms or k in ("dec_g0h", "dec_y0h")}
+                       if bf16_gemms is None or k in bf16_gemms}
             self.bf16_decoder = bf16_decoder
             self.dec_stream = _pack.pack_decoder_stream(packed, hp).to(self.device)
             self.n_slots = _lib.load().fcl_sm_count()
@@ -190,22 +190,26 @@ class Engine:
         return before
 
     def decoder_bf16(self, hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p, dropout_seed):
-        """Tensor-core decoder: hoisted terms in sorted-tile order (transposed), then the persistent tcgen05 loop."""
+        """Tensor-core decoder: h packed as a bf16 operand image in duration-sorted tile order, then the
+        persistent tcgen05 loop."""
         hp, w = self.hp, self.w
         P, E, H, O = hn.shape[0], hp.eunits, hp.dunits, hp.odim
+        n_tiles = (P + 127) // 128
         with self.stage("decoder_hoist"):
-            g0h = self.conv_gemm(hn, None, w["dec_g0h_b"], P, E, 4 * H, 1, ACT_NONE, key="dec_g0h", row_gather=order,
-                                 tile_transposed=True)
-            y0h = self.conv_gemm(hn, None, None, P, E, O, 1, ACT_NONE, key="dec_y0h", row_gather=order,
-                                 tile_transposed=True)
+            hn_img = torch.empty((n_tiles * 128 * E,), dtype=torch.bfloat16, device=self.device)
+            self._call("fcl_pack_rows_bf16", _lib.PackRowsParams(n_rows=P, cols=E, src=dptr(hn), ld=E, order=dptr(order),
+                                                                 dst=dptr(hn_img)))
         before = torch.empty((max(n_frames, 1), O), dtype=torch.float32, device=self.device)
-        p = _lib.DecoderBf16Params(n_rows=P, n_tiles=(P + 127) // 128, n_slots=self.n_slots, dunits=H,
+        trace = getattr(self, "dec_trace", None)
+        p = _lib.DecoderBf16Params(n_rows=P, n_tiles=n_tiles, n_slots=self.n_slots, eunits=E, dunits=H,
                                    prenet_units=hp.prenet_units, odim=O, order=dptr(order), dur=dptr(dur),
                                    frame_off=dptr(frame_off), row_utt=dptr(row_utt), row_phone=dptr(row_phone),
-                                   g0h_t=dptr(g0h), y0h_t=dptr(y0h), w_stream=dptr(self.dec_stream),
+                                   hn_img=dptr(hn_img), w_stream=dptr(self.dec_stream),
                                    bp0=dptr(w["dec_bp0"]), bp1=dptr(w["dec_bp1"]), wpos=dptr(w["dec_wpos"]),
-                                   b1=dptr(w["dec_b1"]), act_ws=dptr(self.dec_act_ws), c_ws=dptr(self.dec_c_ws),
-                                   before=dptr(before), zoneout=zoneout, dropout_p=dropout_p, dropout_seed=dropout_seed)
+                                   b0=dptr(w["dec_g0h_b"]), b1=dptr(w["dec_b1"]), act_ws=dptr(self.dec_act_ws),
+                                   c_ws=dptr(self.dec_c_ws), before=dptr(before), zoneout=zoneout,
+                                   dropout_p=dropout_p, dropout_seed=dropout_seed, trace=dptr(trace),
+                                   trace_cap=(trace.numel() - 2) // 2 if trace is not None else 0)
         with self.stage("decoder_loop"):
             self._call("fcl_decoder_bf16", p)
         return before

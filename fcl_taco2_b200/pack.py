@@ -115,7 +115,7 @@ def pack_conv_bf16(w: torch.Tensor, ntile: int | None = None, kstage: int | None
 
 
 GEMM_KEYS = ["enc_conv0", "enc_conv1", "enc_conv2", "blstm_wih", "dur_conv0", "dur_conv1", "pitch_conv0", "pitch_conv1",
-             "energy_conv0", "energy_conv1", "dec_g0h", "dec_y0h", "post_conv0", "post_conv1", "post_conv2",
+             "energy_conv0", "energy_conv1", "post_conv0", "post_conv1", "post_conv2",
              "post_conv3", "post_conv4"]
 
 
@@ -130,17 +130,23 @@ def pack_bf16(packed_fp32: dict) -> dict:
 
 def pack_decoder_stream(packed_fp32: dict, hp) -> torch.Tensor:
     """bf16 weight stream of the tensor-core decoder, in the order the kernel consumes it each step
-    (csrc/decoder_bf16.cu): prenet.0 (K 80 -> 128 zero-padded) | prenet.1 | cell 0 | cell 1 | feat_out.
-    Every block is the UMMA core-matrix image of one (256-or-odim columns x 64 k) B stage."""
-    U, H, O = hp.prenet_units, hp.dunits, hp.odim
-    assert U == 256 and H % 64 == 0 and O % 16 == 0 and O <= 128
+    (csrc/decoder_bf16.cu): prenet.0 (K 80 -> 128 zero-padded) | prenet.1 |
+    cell 0 rows [prenet part of W_ih0 ; h part of W_ih0 ; W_hh0] | cell 1 rows [W_ih1 ; W_hh1] |
+    feat_out rows [z part ; h part]. Every block is the UMMA core-matrix image of one
+    (256-or-odim columns x 64 k) B stage."""
+    U, H, O, E = hp.prenet_units, hp.dunits, hp.odim, hp.eunits
+    assert U == 256 and H % 64 == 0 and E % 64 == 0 and O % 16 == 0 and O <= 128
     wp0 = torch.zeros(128, U)
     wp0[:O] = packed_fp32["dec_wp0"]
+    w0 = packed_fp32["dec_w0"]                       # rows [prenet part (U) ; W_hh0 (H)], cols 4H gate-interleaved
+    w0h = packed_fp32["dec_g0h_w"][0]                # (E, 4H): h part of W_ih0
+    l0 = torch.cat([w0[:U], w0h, w0[U:]], dim=0)
+    feat = torch.cat([packed_fp32["dec_wf"], packed_fp32["dec_y0h_w"][0]], dim=0)      # (H + E, O)
     parts = [
         pack_conv_bf16(wp0.unsqueeze(0), 256, 64)[0],
         pack_conv_bf16(packed_fp32["dec_wp1"].unsqueeze(0), 256, 64)[0],
-        pack_conv_bf16(packed_fp32["dec_w0"].unsqueeze(0), 256, 64)[0],
+        pack_conv_bf16(l0.unsqueeze(0), 256, 64)[0],
         pack_conv_bf16(packed_fp32["dec_w1"].unsqueeze(0), 256, 64)[0],
-        pack_conv_bf16(packed_fp32["dec_wf"].unsqueeze(0), O, 64)[0],
+        pack_conv_bf16(feat.unsqueeze(0), O, 64)[0],
     ]
     return torch.cat(parts).contiguous()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 5
+#define FCL_ABI_VERSION 6
 
 enum {
   FCL_OK = 0,
@@ -221,28 +221,41 @@ typedef struct {
 } FclDecoderParams;
 int fcl_decoder_f32(const FclDecoderParams* p, void* stream);
 
+/* Row gather + bf16 pack into the UMMA operand image the tensor-core decoder streams:
+ * dst[tile][cols/8][128][8] (bf16) with dst row (tile*128 + i) = src row order[tile*128 + i]; rows beyond
+ * n_rows are zero. Used for the encoder state h (+ pitch/energy embeddings) in duration-sorted order.
+ */
+typedef struct {
+  int32_t n_rows, cols;
+  const float* src;          /* (n_rows, ld) fp32 */
+  int32_t ld;
+  const int32_t* order;      /* (n_rows) */
+  void* dst;                 /* bf16, ceil(n_rows/128) * cols * 128 elements */
+} FclPackRowsParams;
+int fcl_pack_rows_bf16(const FclPackRowsParams* p, void* stream);
+
 /* Tensor-core form of K4 (tcgen05; bf16 operands, fp32 accumulators in TMEM, fp32 cell state).
- * Tiles are 128 duration-sorted rows; a persistent grid of `n_slots` CTAs walks the tiles round-robin.
- *   g0h_t / y0h_t : hoisted terms in SORTED row order, tile-transposed [tile][cols/4][128][4] fp32
- *                   (fcl_conv_gemm_bf16 with row_gather = order and out_layout = 1)
+ * Tiles are 128 duration-sorted rows; a persistent grid of `n_slots` CTAs walks the tiles.
+ *   hn_img        : encoder state of every tile as a bf16 operand image (fcl_pack_rows_bf16); it is a K-slice
+ *                   of the cell-0 and feat_out GEMMs (nothing is hoisted into per-row fp32 tables)
  *   w_stream      : bf16 weights pre-tiled as UMMA core matrices in consumption order
- *                   prenet.0 (K padded 80->128) | prenet.1 | cell 0 [W_ih0 prenet part ; W_hh0] |
- *                   cell 1 [W_ih1 ; W_hh1] | feat_out (fcl_taco2_b200/pack.py: pack_decoder_stream)
+ *                   prenet.0 (K padded 80->128) | prenet.1 | cell 0 [W_ih0 prenet part ; W_ih0 h part ; W_hh0] |
+ *                   cell 1 [W_ih1 ; W_hh1] | feat_out [z part ; h part]  (fcl_taco2_b200/pack.py: pack_decoder_stream)
  *   act_ws / c_ws : per-slot scratch, sizes from fcl_decoder_bf16_workspace()
  */
 typedef struct {
-  int32_t n_rows, n_tiles, n_slots, dunits, prenet_units, odim;
+  int32_t n_rows, n_tiles, n_slots, eunits, dunits, prenet_units, odim;
   const int32_t* order;
   const int32_t* dur;
   const int32_t* frame_off;
   const int32_t* row_utt;
   const int32_t* row_phone;
-  const float* g0h_t;
-  const float* y0h_t;
+  const void* hn_img;
   const void* w_stream;
   const float* bp0;          /* (U) prenet.0 bias                                          */
   const float* bp1;          /* (U) prenet.1 bias                                          */
   const float* wpos;         /* (4H) gate-interleaved position column of W_ih0             */
+  const float* b0;           /* (4H) gate-interleaved b_ih0 + b_hh0                        */
   const float* b1;           /* (4H) gate-interleaved b_ih1 + b_hh1                        */
   void* act_ws;              /* n_slots * act_bytes_per_slot                               */
   float* c_ws;               /* n_slots * c_floats_per_slot                                */
@@ -250,6 +263,8 @@ typedef struct {
   float zoneout;
   float dropout_p;
   uint64_t dropout_seed;
+  int64_t* trace;            /* optional debug timeline of CTA 0: [0] = count (zero it), then (id, clock) pairs */
+  int32_t trace_cap;         /* capacity in records                                         */
 } FclDecoderBf16Params;
 int fcl_decoder_bf16_workspace(int32_t prenet_units, int32_t dunits, int64_t* act_bytes_per_slot,
                                int64_t* c_floats_per_slot);

@@ -4,11 +4,13 @@ The reference prenet applies F.dropout at inference with torch's global RNG
 (nets/modules/decoder_sa.py:156-157), so its output is not reproducible across
 implementations. The B200 path defines the keep decision as a pure function
 
-    keep(seed, utt, phoneme, step, layer, unit) = Philox4x32-10(
-        key     = (seed & 0xffffffff, seed >> 32),
-        counter = (unit >> 2, step | layer << 24, phoneme, utt))[unit & 3] >= thresh(p)
+    words = Philox4x32-10(key = (seed & 0xffffffff, seed >> 32),
+                          counter = (unit >> 3, step | layer << 24, phoneme, utt))
+    j = unit & 7;  lane16 = (words[j >> 1] >> 16) if (j & 1) else (words[j >> 1] & 0xffff)
+    keep(seed, utt, phoneme, step, layer, unit) = lane16 >= thresh16(p)
 
-with thresh(p) = min(floor(float32(p) * 2**32 + 0.5), 2**32 - 1). This file restates that
+with thresh16(p) = min(floor(float32(p) * 65536 + 0.5), 65535): one Philox call decides 8 units
+(16-bit resolution of p; exact for the reference's p = 0.5). This file restates that
 definition on the CPU (the CUDA copy is fcl_taco2_b200/csrc/philox.cuh); the
 oracle injects it into the reference through oracle.ref_loader.prenet_dropout.
 Philox4x32-10 is Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"
@@ -41,18 +43,20 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
 
 
-def threshold(p: float) -> int:
-    """p is taken as float32 (what the CUDA side receives); float32(p) * 2**32 is an integer for p >= 2**-9."""
-    return min(int(float(np.float32(p)) * 4294967296.0 + 0.5), 4294967295)
+def threshold16(p: float) -> int:
+    """p is taken as float32 (what the CUDA side receives): min(floor(float32(p) * 65536 + 0.5), 65535)."""
+    return min(int(np.float32(np.float32(p) * np.float32(65536.0) + np.float32(0.5))), 65535)
 
 
 def keep_mask(seed: int, utt, phoneme, step: int, layer: int, n_units: int, p: float) -> np.ndarray:
     """-> bool (rows, n_units). `utt`, `phoneme`: int arrays (rows,)."""
-    assert n_units % 4 == 0
+    assert n_units % 8 == 0
     utt = np.asarray(utt, dtype=np.uint64).reshape(-1, 1)
     ph = np.asarray(phoneme, dtype=np.uint64).reshape(-1, 1)
-    quad = np.arange(n_units // 4, dtype=np.uint64).reshape(1, -1)
+    octs = np.arange(n_units // 8, dtype=np.uint64).reshape(1, -1)
     c1 = np.uint64((step & 0xFFFFFF) | (layer << 24))
-    w = philox4x32_10(quad, c1, ph, utt, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    words = np.stack(w, axis=-1).reshape(utt.shape[0], n_units)          # unit = 4*quad + j
-    return words >= np.uint32(threshold(p))
+    w = philox4x32_10(octs, c1, ph, utt, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    words = np.stack(w, axis=-1)                                               # (rows, octs, 4)
+    lanes = np.stack([words & np.uint32(0xFFFF), words >> np.uint32(16)], axis=-1)   # (rows, octs, 4, 2): unit j -> [j>>1][j&1]
+    lanes = lanes.reshape(utt.shape[0], n_units)
+    return lanes >= np.uint32(threshold16(p))

@@ -22,4 +22,4 @@ def test_keep_mask_rate_and_invariance():
     # row r of a batch equals the same (utt, phoneme) evaluated alone: batching/sorting invariant
     one = philox.keep_mask(7, [0], [17], 3, 1, 256, 0.5)
     assert (one[0] == m[17]).all()
-    assert philox.threshold(0.5) == 1 << 31 and philox.threshold(1.0) == 0xFFFFFFFF
+    assert philox.threshold16(0.5) == 1 << 15 and philox.threshold16(1.0) == 0xFFFF
