@@ -3,11 +3,16 @@
 // :63-96 (ZoneOutCell around torch.nn.LSTMCell), :398 (feat_out), fused with the ragged gather :619-630.
 //
 // One CTA owns a tile of 128 duration-sorted phoneme rows for all of their steps (rows are independent, so
-// no inter-CTA communication exists). Per step it runs five dependent GEMM phases on the tensor cores
-//   P0 prenet.0 [128 x 80(->128)] x [256]      P1 prenet.1 [128 x 256] x [256]
-//   L0 gates of cell 0: [x2 | h | z0] (K = 256 + E + H) x 4H     L1 gates of cell 1: [z0' | z1] (K = 2H) x 4H
-//   F  feat_out: [z1' | h] (K = H + E) x 80
-// with bf16 operands, fp32 accumulators in TMEM (two 256-column buffers: the epilogue of chunk j overlaps
+// no inter-CTA communication exists). Per step it runs four dependent GEMM phases on the tensor cores
+//   P1 prenet.1: x1 (K = 256) x 256
+//   L0 gates of cell 0: [h | z0 | x2] (K = E + H + 256) x 4H      L1 gates of cell 1: [z1 | z0'] (K = 2H) x 4H
+//   FP [h | z1'] (K = E + H) x {80 feat_out columns ; 256 columns of prenet.0 composed with feat_out}
+// Two algebraic rearrangements keep the dependency chain short: (1) feat_out has no activation, so
+// prenet.0(y) = relu(y Wp0^T + b) = relu([z1'|h] (Wfeat^T Wp0^T) + b): the next step's prenet.0 shares the
+// operand (and the phase) of feat_out; (2) inside every phase the K-slices that are already known (h, the
+// previous step's z) come first and the slice produced by the previous phase comes last, so the MMAs of a
+// phase start while the previous phase's epilogue is still running.
+// All GEMMs use bf16 operands, fp32 accumulators in TMEM (two 256-column buffers: the epilogue of chunk j overlaps
 // the MMAs of chunk j+1), fp32 cell state. The encoder state h of the tile is a K-slice of the A operand
 // (it is NOT hoisted into a per-row fp32 table: re-reading such a table every step made the epilogue
 // latency-bound on HBM). Weights (bf16, pre-tiled as UMMA core matrices, in consumption order) and the
@@ -36,22 +41,20 @@ constexpr int kEpiThreads = 512;
 struct DbShared {
   uint64_t full[kDbStages], empty[kDbStages];
   uint64_t tmem_full[2], tmem_empty[2];
-  uint64_t a_ready[5];        // x0, x1, x2, z0', z1' operand images complete (epilogue -> producer)
+  uint64_t a_ready[4];        // x1, x2, z0', z1' operand images complete (epilogue -> producer)
   uint32_t tmem_base;
-  int steps;
 };
 
-// activation scratch of one CTA slot (bytes)
-__host__ __device__ inline size_t db_x0_off() { return 0; }                                   // K padded to 128
-__host__ __device__ inline size_t db_x1_off() { return 128 * 128 * 2; }
-__host__ __device__ inline size_t db_x2_off(int U) { return db_x1_off() + (size_t)U * 128 * 2; }
+// activation scratch of one CTA slot (bytes): x1 | x2 | z0a z0b z1a z1b
+__host__ __device__ inline size_t db_x1_off() { return 0; }
+__host__ __device__ inline size_t db_x2_off(int U) { return (size_t)U * 128 * 2; }
 __host__ __device__ inline size_t db_z_off(int U, int H, int which /*0..3: z0a z0b z1a z1b*/) {
-  return db_x2_off(U) + (size_t)U * 128 * 2 + (size_t)which * H * 128 * 2;
+  return 2 * (size_t)U * 128 * 2 + (size_t)which * H * 128 * 2;
 }
 __host__ __device__ inline size_t db_act_bytes(int U, int H) { return db_z_off(U, H, 4); }
 
 // tile visited at round `tk` by this CTA: boustrophedon over duration-sorted tiles (longest first), so every
-// CTA gets a similar sum of steps. -1 when done.
+// CTA gets a similar sum of steps. < 0 when done.
 __device__ __forceinline__ int db_tile(int tk, int n_tiles) {
   const int G = gridDim.x, b = blockIdx.x;
   const int t = tk * G + ((tk & 1) ? (G - 1 - b) : b);
@@ -61,7 +64,8 @@ __device__ __forceinline__ int db_tile(int tk, int n_tiles) {
 
 // optional timeline trace of CTA 0 (debug/profiling aid; p.trace == nullptr in production).
 // record = {event id, clock64}; ids: 100+phase*10+chunk (MMA: accumulator free), 200+.. (MMA: first stage landed),
-// 300+.. (MMA: chunk issued), 400+.. (epilogue: accumulator ready), 500+.. (epilogue: chunk done), 600+phase (producer: operand ready)
+// 300+.. (MMA: chunk issued), 400+.. (epilogue: accumulator ready), 500+.. (epilogue: chunk done), 600+phase
+// (producer: phase start). Phases: 0 = P1, 1 = L0, 2 = L1, 3 = FP.
 __device__ __forceinline__ void db_trace(const FclDecoderBf16Params& p, int id) {
   if (p.trace && blockIdx.x == 0) {
     const unsigned long long n = atomicAdd(reinterpret_cast<unsigned long long*>(p.trace), 1ull);
@@ -72,22 +76,62 @@ __device__ __forceinline__ void db_trace(const FclDecoderBf16Params& p, int id) 
   }
 }
 
+struct DbDims {
+  int kU, kH, kE, gate_chunks;
+  __device__ __forceinline__ int nchunks(int phase, bool last_step) const {
+    return phase == 0 ? 1 : phase == 3 ? (last_step ? 1 : 2) : gate_chunks;
+  }
+  __device__ __forceinline__ int kstages(int phase) const {
+    return phase == 0 ? kU : phase == 1 ? kE + kH + kU : phase == 2 ? 2 * kH : kE + kH;
+  }
+  // first K stage (of chunk 0) that needs the operand produced by the previous phase
+  __device__ __forceinline__ int late_stage(int phase) const {
+    return phase == 0 ? 0 : phase == 1 ? kE + kH : phase == 2 ? kH : kE;
+  }
+};
+
+// prenet epilogue for 64 columns of one row: bias, ReLU, counter-based dropout, bf16 operand image
+// (decoder_sa.py:146-158). `acc` == nullptr means a zero pre-activation (the step-0 input frame is zero).
+__device__ __forceinline__ void prenet_store16(const float* v, const float* __restrict__ bias, int col0, int r, uint8_t* dst,
+                                               bool use_drop, uint32_t drop_thr, float drop_scale, uint64_t seed,
+                                               uint32_t utt, uint32_t ph, uint32_t step, uint32_t layer) {
+#pragma unroll
+  for (int h8 = 0; h8 < 2; ++h8) {                         // 8 columns share one Philox call
+    Philox4 rnd = Philox4{0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (use_drop) rnd = dropout_words(seed, utt, ph, step, layer, (uint32_t)((col0 >> 3) + h8));
+    const uint32_t wv[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * h8));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * h8) + 1);
+    const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t u16 = (j & 1) ? (wv[j >> 1] >> 16) : (wv[j >> 1] & 0xFFFFu);
+      const float y = fmaxf((v ? v[8 * h8 + j] : 0.f) + bv[j], 0.f) * drop_scale;
+      x[j] = u16 >= drop_thr ? y : 0.f;
+    }
+    uint4 w;
+    w.x = pack_bf16(x[0], x[1]); w.y = pack_bf16(x[2], x[3]);
+    w.z = pack_bf16(x[4], x[5]); w.w = pack_bf16(x[6], x[7]);
+    *reinterpret_cast<uint4*>(dst + ((size_t)((col0 >> 3) + h8) * 128 + r) * 16) = w;
+  }
+}
+
 __global__ void __launch_bounds__(kDbThreads, 1)
 decoder_bf16_kernel(FclDecoderBf16Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ DbShared sh;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int H = p.dunits, U = p.prenet_units, O = p.odim;
-  const int H4 = 4 * H;
-  const int kU = U / 64, kH = H / 64, kE = p.eunits / 64;   // K stages of the prenet / hidden / encoder-state operands
-  const int gate_chunks = H4 / 256;
+  const int H = p.dunits, U = p.prenet_units, O = p.odim, E = p.eunits;
+  DbDims dm;
+  dm.kU = U / 64; dm.kH = H / 64; dm.kE = E / 64; dm.gate_chunks = 4 * H / 256;
   uint8_t* act = reinterpret_cast<uint8_t*>(p.act_ws) + (size_t)blockIdx.x * db_act_bytes(U, H);
   float* cws = p.c_ws + (size_t)blockIdx.x * 2 * H * 128;
 
   if (tid == 0) {
     for (int s = 0; s < kDbStages; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&sh.tmem_full[b], 1); mbar_init(&sh.tmem_empty[b], kEpiThreads); }
-    for (int i = 0; i < 5; ++i) mbar_init(&sh.a_ready[i], kEpiThreads);
+    for (int i = 0; i < 4; ++i) mbar_init(&sh.a_ready[i], kEpiThreads);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&sh.tmem_base, 512);
@@ -95,40 +139,38 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
-
-  // byte size of one B stage per phase (P0, P1, L0, L1 use 256 columns; F uses O columns)
   const uint32_t b_bytes_wide = 256u * 64u * 2u, b_bytes_feat = (uint32_t)O * 64u * 2u;
 
   if (warp == 0) {
     // ================================================================ producer
     if (elect_one()) {
       uint32_t stage = 0, sphase = 0;                 // ring position / parity
-      uint32_t rdy[5] = {0, 0, 0, 0, 0};              // parity of each a_ready barrier
+      uint32_t rdy[4] = {0, 0, 0, 0};                 // parity of each a_ready barrier
       for (int tk = 0, tile; (tile = db_tile(tk, p.n_tiles)) >= 0; ++tk) {
         const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
-        const uint8_t* himg = reinterpret_cast<const uint8_t*>(p.hn_img) + (size_t)tile * p.eunits * 128 * 2;
+        const uint8_t* himg = reinterpret_cast<const uint8_t*>(p.hn_img) + (size_t)tile * E * 128 * 2;
         for (int m = 0; m < steps; ++m) {
           const int zp = m & 1;
           const uint8_t* z0cur = act + db_z_off(U, H, zp), *z0new = act + db_z_off(U, H, zp ^ 1);
           const uint8_t* z1cur = act + db_z_off(U, H, 2 + zp), *z1new = act + db_z_off(U, H, 2 + (zp ^ 1));
           const uint8_t* wptr = reinterpret_cast<const uint8_t*>(p.w_stream);
-          for (int phase = 0; phase < 5; ++phase) {
-            mbar_wait(&sh.a_ready[phase], rdy[phase]);
-            rdy[phase] ^= 1u;
-            db_trace(p, 600 + phase);
-            const int nchunks = (phase == 2 || phase == 3) ? gate_chunks : 1;
-            const int kst = phase == 0 ? 2 : phase == 1 ? kU : phase == 2 ? kU + kE + kH : phase == 3 ? 2 * kH : kH + kE;
-            const uint32_t bb = phase == 4 ? b_bytes_feat : b_bytes_wide;
-            for (int c = 0; c < nchunks; ++c) {
+          for (int phase = 0; phase < 4; ++phase) {
+            if (tid == 0) db_trace(p, 600 + phase);
+            const int nch = dm.nchunks(phase, m + 1 == steps), kst = dm.kstages(phase), late = dm.late_stage(phase);
+            for (int c = 0; c < nch; ++c) {
+              const uint32_t bb = (phase == 3 && c == 0) ? b_bytes_feat : b_bytes_wide;
               for (int ks = 0; ks < kst; ++ks) {
+                if (c == 0 && ks == late) {            // operand written by the previous phase's epilogue
+                  mbar_wait(&sh.a_ready[phase], rdy[phase]);
+                  rdy[phase] ^= 1u;
+                }
                 const uint8_t* asrc;
-                if (phase == 0) asrc = act + db_x0_off() + (size_t)ks * kABytes;
-                else if (phase == 1) asrc = act + db_x1_off() + (size_t)ks * kABytes;
-                else if (phase == 2) asrc = ks < kU ? act + db_x2_off(U) + (size_t)ks * kABytes
-                                          : ks < kU + kE ? himg + (size_t)(ks - kU) * kABytes
-                                                         : z0cur + (size_t)(ks - kU - kE) * kABytes;
-                else if (phase == 3) asrc = ks < kH ? z0new + (size_t)ks * kABytes : z1cur + (size_t)(ks - kH) * kABytes;
-                else asrc = ks < kH ? z1new + (size_t)ks * kABytes : himg + (size_t)(ks - kH) * kABytes;
+                if (phase == 0) asrc = act + db_x1_off() + (size_t)ks * kABytes;
+                else if (phase == 1) asrc = ks < dm.kE ? himg + (size_t)ks * kABytes
+                                          : ks < dm.kE + dm.kH ? z0cur + (size_t)(ks - dm.kE) * kABytes
+                                                               : act + db_x2_off(U) + (size_t)(ks - dm.kE - dm.kH) * kABytes;
+                else if (phase == 2) asrc = ks < dm.kH ? z1cur + (size_t)ks * kABytes : z0new + (size_t)(ks - dm.kH) * kABytes;
+                else asrc = ks < dm.kE ? himg + (size_t)ks * kABytes : z1new + (size_t)(ks - dm.kE) * kABytes;
                 mbar_wait(&sh.empty[stage], sphase ^ 1u);
                 mbar_arrive_expect_tx(&sh.full[stage], kABytes + bb);
                 uint8_t* st = smem + (size_t)stage * kStageBytes;
@@ -152,13 +194,13 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
       for (int tk = 0, tile; (tile = db_tile(tk, p.n_tiles)) >= 0; ++tk) {
         const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
         for (int m = 0; m < steps; ++m) {
-          for (int phase = 0; phase < 5; ++phase) {
-            const int nchunks = (phase == 2 || phase == 3) ? gate_chunks : 1;
-            const int kst = phase == 0 ? 2 : phase == 1 ? kU : phase == 2 ? kU + kE + kH : phase == 3 ? 2 * kH : kH + kE;
-            const uint32_t ncols = phase == 4 ? (uint32_t)O : 256u;
-            const uint32_t idesc = phase == 4 ? idesc_feat : idesc_wide;
-            const uint32_t b_lbo = ncols * 16u;
-            for (int c = 0; c < nchunks; ++c) {
+          for (int phase = 0; phase < 4; ++phase) {
+            const int nch = dm.nchunks(phase, m + 1 == steps), kst = dm.kstages(phase);
+            for (int c = 0; c < nch; ++c) {
+              const bool feat = phase == 3 && c == 0;
+              const uint32_t ncols = feat ? (uint32_t)O : 256u;
+              const uint32_t idesc = feat ? idesc_feat : idesc_wide;
+              const uint32_t b_lbo = ncols * 16u;
               const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
               mbar_wait(&sh.tmem_empty[buf], (use & 1u) ^ 1u);
               tc_fence_after();
@@ -211,10 +253,13 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
       }
       const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
       if (steps == 0) continue;
-      // ---- tile init: zero x0 (all 16 k-chunks) and the "current" z images; this thread's quarter of the chunks
+      // ---- tile init: x1 of step 0 (the first input frame is zero: prenet.0 sees only its bias) and zero z images
       {
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g)
+          prenet_store16(nullptr, p.bp0, cs * 64 + g * 16, r, act + db_x1_off(), use_drop, drop_thr, drop_scale,
+                         p.dropout_seed, (uint32_t)utt, (uint32_t)ph, 0u, 0u);
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-        for (int kc = cs; kc < 16; kc += 4) *reinterpret_cast<uint4*>(act + db_x0_off() + ((size_t)kc * 128 + r) * 16) = z4;
         for (int kc = cs; kc < H / 8; kc += 4) {
           *reinterpret_cast<uint4*>(act + db_z_off(U, H, 0) + ((size_t)kc * 128 + r) * 16) = z4;
           *reinterpret_cast<uint4*>(act + db_z_off(U, H, 2) + ((size_t)kc * 128 + r) * 16) = z4;
@@ -229,49 +274,26 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
         uint8_t* z1cur = act + db_z_off(U, H, 2 + zp), *z1new = act + db_z_off(U, H, 2 + (zp ^ 1));
         const float pos = (row >= 0 && m < d) ? __fdiv_rn((float)m, (float)d) : 0.f;
 
-        // ---------------- P0, P1: prenet layers (bias, ReLU, dropout) -> x1 / x2 images; 64 columns per thread
-#pragma unroll 1
-        for (int layer = 0; layer < 2; ++layer) {
+        // ---------------- P1: prenet layer 1 (bias, ReLU, dropout) -> x2 image; 64 columns per thread
+        {
           const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
           mbar_wait(&sh.tmem_full[buf], use & 1u);
           tc_fence_after();
-          if (tid == 128) db_trace(p, 400 + layer * 10);
-          const float* bias = layer == 0 ? p.bp0 : p.bp1;
-          uint8_t* dst = act + (layer == 0 ? db_x1_off() : db_x2_off(U));
+          if (tid == 128) db_trace(p, 400);
 #pragma unroll 1
           for (int g = 0; g < 4; ++g) {
             float v[16];
             const int col0 = cs * 64 + g * 16;
             tmem_ld16(lane_addr + buf * 256u + (uint32_t)col0, v);
-#pragma unroll
-            for (int h8 = 0; h8 < 2; ++h8) {                         // 8 columns share one Philox call
-              Philox4 rnd = Philox4{0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-              if (use_drop)
-                rnd = dropout_words(p.dropout_seed, (uint32_t)utt, (uint32_t)ph, (uint32_t)m, (uint32_t)layer,
-                                    (uint32_t)((col0 >> 3) + h8));
-              const uint32_t wv[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-              const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * h8));
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * h8) + 1);
-              const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-              float x[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint32_t u16 = (j & 1) ? (wv[j >> 1] >> 16) : (wv[j >> 1] & 0xFFFFu);
-                const float y = fmaxf(v[8 * h8 + j] + bv[j], 0.f) * drop_scale;
-                x[j] = u16 >= drop_thr ? y : 0.f;
-              }
-              uint4 w;
-              w.x = pack_bf16(x[0], x[1]); w.y = pack_bf16(x[2], x[3]);
-              w.z = pack_bf16(x[4], x[5]); w.w = pack_bf16(x[6], x[7]);
-              *reinterpret_cast<uint4*>(dst + ((size_t)((col0 >> 3) + h8) * 128 + r) * 16) = w;
-            }
+            prenet_store16(v, p.bp1, col0, r, act + db_x2_off(U), use_drop, drop_thr, drop_scale, p.dropout_seed,
+                           (uint32_t)utt, (uint32_t)ph, (uint32_t)m, 1u);
           }
           tc_fence_before();
           mbar_arrive(&sh.tmem_empty[buf]);
           ++chunk_ctr;
           fence_proxy_async_all();
-          mbar_arrive(&sh.a_ready[1 + layer]);
-          if (tid == 128) db_trace(p, 500 + layer * 10);
+          mbar_arrive(&sh.a_ready[1]);
+          if (tid == 128) db_trace(p, 500);
         }
 
         // ---------------- L0, L1: zoneout LSTM cells; per chunk this thread owns 16 hidden units of its row.
@@ -293,9 +315,9 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
             z_cur[1] = __ldcg(reinterpret_cast<const uint4*>(zcur + ((size_t)((u0 >> 3) + 1) * 128 + r) * 16));
           }
 #pragma unroll 1
-          for (int c = 0; c < gate_chunks; ++c) {
+          for (int c = 0; c < dm.gate_chunks; ++c) {
             const int u0 = c * 64 + cs * 16;                          // first of this thread's 16 hidden units
-            if (c + 1 < gate_chunks) {
+            if (c + 1 < dm.gate_chunks) {
               const int un = u0 + 64;
 #pragma unroll
               for (int j = 0; j < 16; ++j) c_nxt[j] = m == 0 ? 0.f : __ldcg(cl + (size_t)(un + j) * 128 + r);
@@ -305,7 +327,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
             const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
             mbar_wait(&sh.tmem_full[buf], use & 1u);
             tc_fence_after();
-            if (tid == 128) db_trace(p, 400 + (2 + layer) * 10 + c);
+            if (tid == 128) db_trace(p, 400 + (1 + layer) * 10 + c);
             uint32_t zout[8];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {                             // 4 units (16 accumulator columns) at a time
@@ -340,45 +362,55 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
             ++chunk_ctr;
             *reinterpret_cast<uint4*>(znew + ((size_t)(u0 >> 3) * 128 + r) * 16) = make_uint4(zout[0], zout[1], zout[2], zout[3]);
             *reinterpret_cast<uint4*>(znew + ((size_t)((u0 >> 3) + 1) * 128 + r) * 16) = make_uint4(zout[4], zout[5], zout[6], zout[7]);
-            if (tid == 128) db_trace(p, 500 + (2 + layer) * 10 + c);
+            if (tid == 128) db_trace(p, 500 + (1 + layer) * 10 + c);
 #pragma unroll
             for (int j = 0; j < 16; ++j) c_cur[j] = c_nxt[j];
             z_cur[0] = z_nxt[0]; z_cur[1] = z_nxt[1];
           }
           fence_proxy_async_all();
-          mbar_arrive(&sh.a_ready[3 + layer]);
+          mbar_arrive(&sh.a_ready[2 + layer]);
         }
 
-        // ---------------- F: feat_out -> output frame (ragged store) and x0 image; 16-column groups, group g -> warp set g % 4
+        // ---------------- FP chunk 0: feat_out -> output frame, stored straight to its final (ragged) position
         {
           const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
           mbar_wait(&sh.tmem_full[buf], use & 1u);
           tc_fence_after();
-          if (tid == 128) db_trace(p, 440);
-          for (int g = cs; g < O / 16; g += 4) {
+          if (tid == 128) db_trace(p, 430);
+          for (int g = cs; g < O / 16; g += 4) {                     // 16-column groups dealt over the 4 column sets
             float v[16];
             tmem_ld16(lane_addr + buf * 256u + (uint32_t)(g * 16), v);
-            if (row >= 0 && m < d) {                               // exhausted rows are masked (decoder_sa.py:625-629)
+            if (row >= 0 && m < d) {                                 // exhausted rows are masked (decoder_sa.py:625-629)
               float4* o = reinterpret_cast<float4*>(p.before + ((size_t)foff + m) * O + g * 16);
 #pragma unroll
               for (int qd = 0; qd < 4; ++qd) o[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
-            }
-#pragma unroll
-            for (int k8 = 0; k8 < 2; ++k8) {
-              uint4 w;
-              w.x = pack_bf16(v[8 * k8], v[8 * k8 + 1]); w.y = pack_bf16(v[8 * k8 + 2], v[8 * k8 + 3]);
-              w.z = pack_bf16(v[8 * k8 + 4], v[8 * k8 + 5]); w.w = pack_bf16(v[8 * k8 + 6], v[8 * k8 + 7]);
-              *reinterpret_cast<uint4*>(act + db_x0_off() + ((size_t)(g * 2 + k8) * 128 + r) * 16) = w;
             }
           }
           tc_fence_before();
           mbar_arrive(&sh.tmem_empty[buf]);
           ++chunk_ctr;
-          if (m + 1 < steps) {
-            fence_proxy_async_all();
-            mbar_arrive(&sh.a_ready[0]);
+          if (tid == 128) db_trace(p, 530);
+        }
+        // ---------------- FP chunk 1: prenet layer 0 of the NEXT step (composed with feat_out) -> x1 image
+        if (m + 1 < steps) {
+          const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
+          mbar_wait(&sh.tmem_full[buf], use & 1u);
+          tc_fence_after();
+          if (tid == 128) db_trace(p, 431);
+#pragma unroll 1
+          for (int g = 0; g < 4; ++g) {
+            float v[16];
+            const int col0 = cs * 64 + g * 16;
+            tmem_ld16(lane_addr + buf * 256u + (uint32_t)col0, v);
+            prenet_store16(v, p.bp0, col0, r, act + db_x1_off(), use_drop, drop_thr, drop_scale, p.dropout_seed,
+                           (uint32_t)utt, (uint32_t)ph, (uint32_t)(m + 1), 0u);
           }
-          if (tid == 128) db_trace(p, 540);
+          tc_fence_before();
+          mbar_arrive(&sh.tmem_empty[buf]);
+          ++chunk_ctr;
+          fence_proxy_async_all();
+          mbar_arrive(&sh.a_ready[0]);
+          if (tid == 128) db_trace(p, 531);
         }
       }
     }

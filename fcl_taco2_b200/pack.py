@@ -130,23 +130,28 @@ def pack_bf16(packed_fp32: dict) -> dict:
 
 def pack_decoder_stream(packed_fp32: dict, hp) -> torch.Tensor:
     """bf16 weight stream of the tensor-core decoder, in the order the kernel consumes it each step
-    (csrc/decoder_bf16.cu): prenet.0 (K 80 -> 128 zero-padded) | prenet.1 |
-    cell 0 rows [prenet part of W_ih0 ; h part of W_ih0 ; W_hh0] | cell 1 rows [W_ih1 ; W_hh1] |
-    feat_out rows [z part ; h part]. Every block is the UMMA core-matrix image of one
-    (256-or-odim columns x 64 k) B stage."""
+    (csrc/decoder_bf16.cu):
+        P1  prenet.1                                   rows [x1]            256 cols
+        L0  cell 0 gates (gate-interleaved)            rows [h ; z0 ; x2]   4H cols
+        L1  cell 1 gates                               rows [z1 ; z0']      4H cols
+        F   feat_out                                   rows [h ; z1']       odim cols
+        PC  prenet.0 composed with feat_out            rows [h ; z1']       256 cols
+    PC = W_feat^T W_p0^T: feat_out has no activation, so prenet.0(y) = relu([z1'|h] PC + b_p0) (fp32 product,
+    rounded to bf16 once). Every block is the UMMA core-matrix image of one (256-or-odim columns x 64 k) B stage."""
     U, H, O, E = hp.prenet_units, hp.dunits, hp.odim, hp.eunits
     assert U == 256 and H % 64 == 0 and E % 64 == 0 and O % 16 == 0 and O <= 128
-    wp0 = torch.zeros(128, U)
-    wp0[:O] = packed_fp32["dec_wp0"]
     w0 = packed_fp32["dec_w0"]                       # rows [prenet part (U) ; W_hh0 (H)], cols 4H gate-interleaved
     w0h = packed_fp32["dec_g0h_w"][0]                # (E, 4H): h part of W_ih0
-    l0 = torch.cat([w0[:U], w0h, w0[U:]], dim=0)
-    feat = torch.cat([packed_fp32["dec_wf"], packed_fp32["dec_y0h_w"][0]], dim=0)      # (H + E, O)
+    l0 = torch.cat([w0h, w0[U:], w0[:U]], dim=0)     # [h ; z0 ; x2]
+    w1 = packed_fp32["dec_w1"]                       # rows [W_ih1 (z0') ; W_hh1 (z1)]
+    l1 = torch.cat([w1[H:], w1[:H]], dim=0)          # [z1 ; z0']
+    feat = torch.cat([packed_fp32["dec_y0h_w"][0], packed_fp32["dec_wf"]], dim=0)      # (E + H, O) rows [h ; z1']
+    pc = (feat.double() @ packed_fp32["dec_wp0"].double()).float()                      # (E + H, U)
     parts = [
-        pack_conv_bf16(wp0.unsqueeze(0), 256, 64)[0],
         pack_conv_bf16(packed_fp32["dec_wp1"].unsqueeze(0), 256, 64)[0],
         pack_conv_bf16(l0.unsqueeze(0), 256, 64)[0],
-        pack_conv_bf16(packed_fp32["dec_w1"].unsqueeze(0), 256, 64)[0],
+        pack_conv_bf16(l1.unsqueeze(0), 256, 64)[0],
         pack_conv_bf16(feat.unsqueeze(0), O, 64)[0],
+        pack_conv_bf16(pc.unsqueeze(0), 256, 64)[0],
     ]
     return torch.cat(parts).contiguous()
