@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -38,7 +38,7 @@ class ConvGemmBf16Params(C.Structure):
     _fields_ = [("rows", i32), ("cin", i32), ("cout", i32), ("taps", i32), ("a", ptr), ("lda", i32),
                 ("gather", ptr), ("row_gather", ptr), ("seg_lo", ptr), ("seg_hi", ptr), ("w_packed", ptr),
                 ("ntile", i32), ("kstage", i32), ("bias", ptr), ("residual", ptr), ("ldr", i32), ("out", ptr),
-                ("ldo", i32), ("act", i32), ("out_layout", i32)]
+                ("ldo", i32), ("act", i32)]
 
 
 class LayerNormParams(C.Structure):

@@ -49,54 +49,72 @@ conv_gemm_bf16_kernel(FclConvGemmBf16Params p, int stages) {
 
   if (warp < 4) {
     // ------------------------------------------------ A producer
-    const int r = tid;
-    const int grow = m0 + r;
-    const bool row_ok = grow < p.rows;
-    int seg_lo = 0, seg_hi = 0x7fffffff;
-    if (row_ok && p.seg_lo) { seg_lo = p.seg_lo[grow]; seg_hi = p.seg_hi[grow]; }
+    // Coalesced loads: one warp instruction covers 8 rows x 64 contiguous bytes (lane & 7 -> row, lane >> 3 ->
+    // 16-byte column), so every 32-byte sector fetched is fully used; a thread then owns 4 consecutive k of a
+    // row and stores them as 8 bytes of that row's 16-byte core-matrix line (conflict-free within 16 lanes).
+    const int lane = tid & 31;
+    const int kq = lane >> 3;                           // which float4 of a 16-float group
     const int half = p.taps >> 1;
+    int rloc[4], grow4[4], lo4[4], hi4[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      rloc[g] = warp * 32 + g * 8 + (lane & 7);
+      grow4[g] = m0 + rloc[g];
+      lo4[g] = 0; hi4[g] = grow4[g] < p.rows ? 0x7fffffff : 0;           // hi = 0 masks rows beyond the matrix
+      if (grow4[g] < p.rows && p.seg_lo) { lo4[g] = p.seg_lo[grow4[g]]; hi4[g] = p.seg_hi[grow4[g]]; }
+    }
+    const int kgroups = kstage >> 4;                    // 16-float groups per stage (<= 5)
     for (int it = 0; it < iters; ++it) {
       const int s = it % stages;
       const uint32_t ph = (uint32_t)(it / stages) & 1u;
       const int t = it / kchunks, kc = (it - t * kchunks) * kstage;
-      const int src = grow + t - half;
-      const bool valid = row_ok && src >= seg_lo && src < seg_hi;
-      const float* base = nullptr;
-      if (valid) {
-        const size_t arow = p.gather ? (size_t)p.gather[src] : p.row_gather ? (size_t)p.row_gather[src] : (size_t)src;
-        base = p.a + arow * p.lda + kc;
-      }
-      // issue all global loads of the stage before touching shared memory (memory-level parallelism)
-      float4 v[20];                                   // kstage <= 80 -> 20 float4
+      float4 v[4][5];
 #pragma unroll
-      for (int j = 0; j < 20; ++j) {
-        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j * 4 < kstage && valid) v[j] = __ldg(reinterpret_cast<const float4*>(base) + j);
+      for (int g = 0; g < 4; ++g) {
+        const int src = grow4[g] + t - half;
+        const bool valid = src >= lo4[g] && src < hi4[g];
+        const float* base = nullptr;
+        if (valid) {
+          const size_t arow = p.gather ? (size_t)p.gather[src] : p.row_gather ? (size_t)p.row_gather[src] : (size_t)src;
+          base = p.a + arow * p.lda + kc + 4 * kq;
+        }
+#pragma unroll
+        for (int kg = 0; kg < 5; ++kg) {
+          v[g][kg] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kg < kgroups && valid) v[g][kg] = __ldg(reinterpret_cast<const float4*>(base + 16 * kg));
+        }
       }
       mbar_wait(&empty_bar[s], ph ^ 1u);
-      uint8_t* a_s = smem + (size_t)s * stage_bytes + (size_t)r * 16;
+      uint8_t* a_s = smem + (size_t)s * stage_bytes;
 #pragma unroll
-      for (int j = 0; j < 10; ++j) {
-        if (j * 8 < kstage) {
-          uint4 w;
-          w.x = pack_bf16(v[2 * j].x, v[2 * j].y); w.y = pack_bf16(v[2 * j].z, v[2 * j].w);
-          w.z = pack_bf16(v[2 * j + 1].x, v[2 * j + 1].y); w.w = pack_bf16(v[2 * j + 1].z, v[2 * j + 1].w);
-          *reinterpret_cast<uint4*>(a_s + (size_t)j * 2048) = w;
+      for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int kg = 0; kg < 5; ++kg) {
+          if (kg < kgroups) {
+            const int slab = 2 * kg + (kq >> 1);        // k / 8 with k = 16 kg + 4 kq
+            *reinterpret_cast<uint2*>(a_s + (size_t)slab * 2048 + (size_t)rloc[g] * 16 + (kq & 1) * 8) =
+                make_uint2(pack_bf16(v[g][kg].x, v[g][kg].y), pack_bf16(v[g][kg].z, v[g][kg].w));
+          }
         }
       }
       fence_proxy_async_smem();
       mbar_arrive(&full_bar[s]);
     }
     // ------------------------------------------------ epilogue
+    // TMEM -> registers (thread = row) -> bias/activation -> this warp's shared-memory patch (the pipeline
+    // stages are idle by now) -> coalesced rows (16 lanes x 16 B per row) + residual -> HBM.
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
     const int n0 = nt * ntile;
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int g = 0; g < ntile / 16; ++g) {
-      float acc[16];
-      tmem_ld16(lane_addr + (uint32_t)(g * 16), acc);
-      if (row_ok || p.out_layout == 1) {
-        const int n = n0 + g * 16;
+    constexpr int kPatchLd = 68;                                          // floats per patch row (64 + pad)
+    float* patch = reinterpret_cast<float*>(smem) + (size_t)warp * 32 * kPatchLd;
+    for (int c0 = 0; c0 < ntile; c0 += 64) {
+      const int sw = min(64, ntile - c0);
+      for (int g = 0; g < sw / 16; ++g) {
+        float acc[16];
+        tmem_ld16(lane_addr + (uint32_t)(c0 + g * 16), acc);
+        const int n = n0 + c0 + g * 16;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float4 o = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
@@ -106,16 +124,27 @@ conv_gemm_bf16_kernel(FclConvGemmBf16Params p, int stages) {
           }
           if (p.act == FCL_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
           else if (p.act == FCL_ACT_TANH) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
-          if (p.residual && row_ok) {
-            const float4 rr = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)grow * p.ldr + n) + q);
-            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-          }
-          if (p.out_layout == 0)
-            reinterpret_cast<float4*>(p.out + (size_t)grow * p.ldo + n)[q] = o;
-          else   // tile-transposed [row tile][cout/4][128][4]: a warp stores 512 contiguous bytes
-            *reinterpret_cast<float4*>(p.out + (((size_t)blockIdx.x * (p.cout >> 2) + ((n >> 2) + q)) * 128 + r) * 4) = o;
+          *reinterpret_cast<float4*>(patch + lane * kPatchLd + g * 16 + q * 4) = o;
         }
       }
+      __syncwarp();
+      const int col = (lane & 15) * 4;
+      if (col < sw) {
+#pragma unroll 4
+        for (int rr = 0; rr < 32; rr += 2) {
+          const int rl = rr + (lane >> 4);
+          const int grow = m0 + warp * 32 + rl;
+          if (grow < p.rows) {
+            float4 o = *reinterpret_cast<const float4*>(patch + rl * kPatchLd + col);
+            if (p.residual) {
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)grow * p.ldr + n0 + c0 + col));
+              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+            }
+            *reinterpret_cast<float4*>(p.out + (size_t)grow * p.ldo + n0 + c0 + col) = o;
+          }
+        }
+      }
+      __syncwarp();
     }
   } else if (warp == 4) {
     // ------------------------------------------------ B producer
@@ -176,7 +205,8 @@ extern "C" int fcl_conv_gemm_bf16(const FclConvGemmBf16Params* p, void* stream) 
   if (stages < 2) stages = (int)((216 * 1024) / stage_bytes);
   stages = stages > kMaxStages ? kMaxStages : stages;
   FCL_REQUIRE(stages >= 2, "tile too large for two pipeline stages");
-  const size_t smem = stage_bytes * stages;
+  size_t smem = stage_bytes * stages;
+  if (smem < 4 * 32 * 68 * sizeof(float)) smem = 4 * 32 * 68 * sizeof(float);   // epilogue staging patches
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);

@@ -75,10 +75,9 @@ class Engine:
         self.launches += 1
 
     def conv_gemm(self, a, w, bias, rows, cin, cout, taps, act, seg=None, gather=None, residual=None, out=None,
-                  lda=None, key=None, row_gather=None, tile_transposed=False):
+                  lda=None, key=None, row_gather=None):
         if out is None:
-            n_out = (rows + 127) // 128 * 128 if tile_transposed else rows
-            out = torch.empty((n_out, cout), dtype=torch.float32, device=self.device)
+            out = torch.empty((rows, cout), dtype=torch.float32, device=self.device)
         if key is not None and key in self.wb:
             wp, ntile, kstage = self.wb[key]
             p = _lib.ConvGemmBf16Params(rows=rows, cin=cin, cout=cout, taps=taps, a=dptr(a), lda=lda or cin,
@@ -86,7 +85,7 @@ class Engine:
                                         seg_lo=dptr(seg[0]) if seg else None,
                                         seg_hi=dptr(seg[1]) if seg else None, w_packed=dptr(wp), ntile=ntile,
                                         kstage=kstage, bias=dptr(bias), residual=dptr(residual), ldr=cout,
-                                        out=dptr(out), ldo=cout, act=act, out_layout=1 if tile_transposed else 0)
+                                        out=dptr(out), ldo=cout, act=act)
             self._call("fcl_conv_gemm_bf16", p)
             return out
         p = _lib.ConvGemmParams(rows=rows, cin=cin, cout=cout, taps=taps, a=dptr(a), lda=lda or cin,

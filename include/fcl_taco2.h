@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 6
+#define FCL_ABI_VERSION 7
 
 enum {
   FCL_OK = 0,
@@ -126,8 +126,6 @@ typedef struct {
   float* out;
   int32_t ldo;
   int32_t act;
-  int32_t out_layout;        /* 0: row-major (rows, ldo). 1: tile-transposed [rows/128][cout/4][128][4]
-                                (what the tensor-core decoder reads; rows padded to full tiles) */
 } FclConvGemmBf16Params;
 int fcl_conv_gemm_bf16(const FclConvGemmBf16Params* p, void* stream);
 
