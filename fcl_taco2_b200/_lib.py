@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -38,7 +38,7 @@ class ConvGemmBf16Params(C.Structure):
     _fields_ = [("rows", i32), ("cin", i32), ("cout", i32), ("taps", i32), ("a", ptr), ("lda", i32),
                 ("gather", ptr), ("row_gather", ptr), ("seg_lo", ptr), ("seg_hi", ptr), ("w_packed", ptr),
                 ("ntile", i32), ("kstage", i32), ("bias", ptr), ("residual", ptr), ("ldr", i32), ("out", ptr),
-                ("ldo", i32), ("act", i32)]
+                ("ldo", i32), ("act", i32), ("out_bf16", i32)]
 
 
 class LayerNormParams(C.Structure):
@@ -72,12 +72,17 @@ class DecoderBf16Params(C.Structure):
                 ("zoneout", f32), ("dropout_p", f32), ("dropout_seed", u64), ("trace", ptr), ("trace_cap", i32)]
 
 
+class BiLstmBf16Params(C.Structure):
+    _fields_ = [("n_utts", i32), ("hidden", i32), ("utt_off", ptr), ("gx", ptr), ("whh_packed", ptr), ("c_ws", ptr),
+                ("out", ptr)]
+
+
 class PackRowsParams(C.Structure):
     _fields_ = [("n_rows", i32), ("cols", i32), ("src", ptr), ("ld", i32), ("order", ptr), ("dst", ptr)]
 
 
 STRUCTS = [LenRegParams, FrameMapParams, ConvGemmParams, LayerNormParams, EmbedAddParams, BiLstmParams,
-           DecoderParams, ConvGemmBf16Params, DecoderBf16Params, PackRowsParams]
+           DecoderParams, ConvGemmBf16Params, DecoderBf16Params, PackRowsParams, BiLstmBf16Params]
 
 ENTRY_POINTS = {
     "fcl_len_reg_scan": LenRegParams,
@@ -90,6 +95,7 @@ ENTRY_POINTS = {
     "fcl_conv_gemm_bf16": ConvGemmBf16Params,
     "fcl_decoder_bf16": DecoderBf16Params,
     "fcl_pack_rows_bf16": PackRowsParams,
+    "fcl_bilstm_bf16": BiLstmBf16Params,
 }
 PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_last_error", "fcl_sm_count", "fcl_struct_size",
                  "fcl_decoder_bf16_workspace"]

@@ -1,0 +1,220 @@
+// Encoder BiLSTM recurrence on the tensor cores (tcgen05).
+// torch.nn.LSTM(E, E/2, 1, bidirectional) of the reference (nets/modules/encoder_sa.py:96-100,143-146), every
+// utterance of the batch independently, packed-sequence semantics (the backward direction starts at the last
+// valid phoneme of each utterance).
+//
+// CTA = (tile of 128 utterances, direction). The batch planner orders utterances longest-first, so a tile
+// runs for the length of its first utterance and rows drop out as they finish. Per time step
+//   gates[128 x 4H] = gx[t] (input projection, precomputed by fcl_conv_gemm_bf16, bf16) + h[128 x H] W_hh^T
+// is one M=128 tcgen05 GEMM in 256-column chunks (gate-interleaved columns, two TMEM accumulator buffers so the
+// epilogue of chunk j overlaps the MMAs of chunk j+1). h lives in shared memory as a bf16 UMMA operand image
+// (double-buffered, written by the epilogue warps: generic->async proxy fence + mbarrier), the cell state in a
+// global fp32 scratch, W_hh streams from L2 through a bulk-copy ring (for H = 128 the ring holds all of it).
+// The step chain is latency/MUFU-bound (5 transcendental per cell), not tensor-bound.
+//
+// Warp roles (640 threads): warp 0 = W_hh bulk-copy producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-19 = epilogue (TMEM lane quarter = warp % 4 -> utterance row; column quarter = (warp-4)/4 -> 16 units).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace fcl {
+using namespace umma;
+
+constexpr int kBlThreads = 640;
+constexpr int kBlEpiThreads = 512;
+constexpr uint32_t kBlBBytes = 256u * 64u * 2u;          // one W_hh stage: 256 gate columns x 64 k
+
+struct BlShared {
+  uint64_t full[4], empty[4];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t h_ready;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kBlThreads, 1)
+bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ BlShared sh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = p.hidden, dir = blockIdx.y, tile = blockIdx.x;
+  const int kH = H / 64, nch = 4 * H / 256;
+  const uint32_t himg_bytes = (uint32_t)H * 256u;         // [H/8][128][8] bf16
+  uint8_t* himg = smem + (size_t)stages * kBlBBytes;       // two h images after the ring
+
+  const int u_first = tile * 128;
+  __shared__ int s_steps;
+  if (tid == 0) s_steps = 0;
+  __syncthreads();
+  if (tid < 128 && u_first + tid < p.n_utts) atomicMax(&s_steps, p.utt_off[u_first + tid + 1] - p.utt_off[u_first + tid]);
+  __syncthreads();
+  const int steps = s_steps;                             // longest utterance of the tile
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&sh.tmem_full[b], 1); mbar_init(&sh.tmem_empty[b], kBlEpiThreads); }
+    mbar_init(&sh.h_ready, kBlEpiThreads);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&sh.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+
+  if (warp == 0) {
+    // ================================================================ W_hh producer (independent of h)
+    if (elect_one()) {
+      uint32_t stage = 0, sphase = 0;
+      const uint8_t* wdir = reinterpret_cast<const uint8_t*>(p.whh_packed) + (size_t)dir * nch * kH * kBlBBytes;
+      for (int t = 0; t < steps; ++t) {
+        const uint8_t* wptr = wdir;
+        for (int i = 0; i < nch * kH; ++i) {
+          mbar_wait(&sh.empty[stage], sphase ^ 1u);
+          mbar_arrive_expect_tx(&sh.full[stage], kBlBBytes);
+          bulk_g2s(smem + (size_t)stage * kBlBBytes, wptr, kBlBBytes, &sh.full[stage]);
+          wptr += kBlBBytes;
+          if (++stage == (uint32_t)stages) { stage = 0; sphase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (elect_one()) {
+      uint32_t stage = 0, sphase = 0, chunk_ctr = 0;
+      const uint32_t idesc = idesc_bf16_f32(128u, 256u);
+      for (int t = 0; t < steps; ++t) {
+        mbar_wait(&sh.h_ready, (uint32_t)t & 1u);          // h(t-1) image complete (t = 0: zeros)
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(himg + (size_t)(t & 1) * himg_bytes);
+        for (int c = 0; c < nch; ++c) {
+          const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
+          mbar_wait(&sh.tmem_empty[buf], (use & 1u) ^ 1u);
+          tc_fence_after();
+          for (int ks = 0; ks < kH; ++ks) {
+            mbar_wait(&sh.full[stage], sphase);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(smem + (size_t)stage * kBlBBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = smem_desc(a_base + (uint32_t)(ks * 4 + k) * 4096u, 2048u, 128u);
+              const uint64_t bd = smem_desc(b_addr + (uint32_t)k * 8192u, 4096u, 128u);
+              mma_bf16_ss(tmem + buf * 256u, ad, bd, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+            }
+            mma_commit(&sh.empty[stage]);
+            if (++stage == (uint32_t)stages) { stage = 0; sphase ^= 1u; }
+          }
+          mma_commit(&sh.tmem_full[buf]);
+          ++chunk_ctr;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ================================================================ epilogue
+    const int q = warp & 3, cs = (warp - 4) >> 2;
+    const int r = q * 32 + lane;                           // utterance row of the tile == TMEM lane
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    const int u = u_first + r;
+    int off = 0, len = 0;
+    if (u < p.n_utts) { off = p.utt_off[u]; len = p.utt_off[u + 1] - off; }
+    float* cst = p.c_ws + ((size_t)(tile * 2 + dir) * H) * 128;        // [H][128]
+    const size_t gx_ld = (size_t)8 * H;                                // bf16 elements per gx row
+    uint32_t chunk_ctr = 0;
+
+    // zero the first h image (this thread's quarter of the k-chunks)
+    for (int kc = cs; kc < H / 8; kc += 4) *reinterpret_cast<uint4*>(himg + ((size_t)kc * 128 + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    mbar_arrive(&sh.h_ready);
+
+    for (int t = 0; t < steps; ++t) {
+      const bool active = t < len;
+      const int grow = off + (dir == 0 ? t : len - 1 - t);
+      uint8_t* hnew = himg + (size_t)((t + 1) & 1) * himg_bytes;
+      const __nv_bfloat16* gxr = reinterpret_cast<const __nv_bfloat16*>(p.gx) + (size_t)grow * gx_ld + (size_t)dir * 4 * H;
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c) {
+        const int u0 = c * 64 + cs * 16;                   // first of this thread's 16 hidden units
+        // request the global operands before waiting for the accumulator
+        uint4 gxv[8];
+        float cold[16];
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gxv[j] = __ldg(reinterpret_cast<const uint4*>(gxr + 4 * u0) + j);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) cold[j] = t == 0 ? 0.f : __ldcg(cst + (size_t)(u0 + j) * 128 + r);
+          if (t + 1 < len) {                               // pull the next step's gx line into L2
+            const __nv_bfloat16* nx = reinterpret_cast<const __nv_bfloat16*>(p.gx) + (size_t)(grow + (dir == 0 ? 1 : -1)) * gx_ld + (size_t)dir * 4 * H + 4 * u0;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+          }
+        }
+        const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
+        mbar_wait(&sh.tmem_full[buf], use & 1u);
+        tc_fence_after();
+        uint32_t hout[8];
+        float hf[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {                      // 4 units (16 accumulator columns) at a time
+          float v[16];
+          tmem_ld16(lane_addr + buf * 256u + (uint32_t)(cs * 64 + g * 16), v);
+          if (active) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int ul = g * 4 + j;
+              const uint4 gq = gxv[ul >> 1];               // 8 bf16 = 2 units x 4 gates
+              const uint32_t w0 = (ul & 1) ? gq.z : gq.x, w1 = (ul & 1) ? gq.w : gq.y;
+              const float gi = __uint_as_float(w0 << 16), gf = __uint_as_float(w0 & 0xFFFF0000u);
+              const float gg = __uint_as_float(w1 << 16), go = __uint_as_float(w1 & 0xFFFF0000u);
+              const float ig = sigmoid_fast(v[4 * j] + gi), fg = sigmoid_fast(v[4 * j + 1] + gf);
+              const float cg = tanh_fast(v[4 * j + 2] + gg), og = sigmoid_fast(v[4 * j + 3] + go);
+              const float cn = fmaf(fg, cold[ul], ig * cg);
+              hf[ul] = og * tanh_fast(cn);
+              cst[(size_t)(u0 + ul) * 128 + r] = cn;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hf[g * 4 + j] = 0.f;
+          }
+          hout[2 * g] = pack_bf16(hf[g * 4], hf[g * 4 + 1]);
+          hout[2 * g + 1] = pack_bf16(hf[g * 4 + 2], hf[g * 4 + 3]);
+        }
+        tc_fence_before();
+        mbar_arrive(&sh.tmem_empty[buf]);
+        ++chunk_ctr;
+        *reinterpret_cast<uint4*>(hnew + ((size_t)(u0 >> 3) * 128 + r) * 16) = make_uint4(hout[0], hout[1], hout[2], hout[3]);
+        *reinterpret_cast<uint4*>(hnew + ((size_t)((u0 >> 3) + 1) * 128 + r) * 16) = make_uint4(hout[4], hout[5], hout[6], hout[7]);
+        if (active) {
+          float4* o = reinterpret_cast<float4*>(p.out + (size_t)grow * 2 * H + (size_t)dir * H + u0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = make_float4(hf[4 * j], hf[4 * j + 1], hf[4 * j + 2], hf[4 * j + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&sh.h_ready);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace fcl
+
+extern "C" int fcl_bilstm_bf16(const FclBiLstmBf16Params* p, void* stream) {
+  using namespace fcl;
+  FCL_REQUIRE(p && p->utt_off && p->gx && p->whh_packed && p->c_ws && p->out, "null pointer");
+  FCL_REQUIRE(p->n_utts > 0, "empty batch");
+  FCL_REQUIRE(p->hidden % 64 == 0 && p->hidden >= 64 && p->hidden <= 256, "hidden must be 64, 128, 192 or 256");
+  const int stages = p->hidden <= 128 ? 4 : 3;
+  const size_t smem = (size_t)stages * kBlBBytes + 2 * (size_t)p->hidden * 256;
+  FCL_REQUIRE(smem <= 226 * 1024, "shared memory budget exceeded");
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(bilstm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("fcl_bilstm_bf16: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
+    attr_smem = smem;
+  }
+  dim3 grid((p->n_utts + 127) / 128, 2);
+  bilstm_bf16_kernel<<<grid, kBlThreads, smem, as_stream(stream)>>>(*p, stages);
+  return check_launch("fcl_bilstm_bf16");
+}

@@ -46,6 +46,7 @@ extern "C" int fcl_struct_size(int which) {
     case 7: return (int)sizeof(FclConvGemmBf16Params);
     case 8: return (int)sizeof(FclDecoderBf16Params);
     case 9: return (int)sizeof(FclPackRowsParams);
+    case 10: return (int)sizeof(FclBiLstmBf16Params);
     default: return -1;
   }
 }

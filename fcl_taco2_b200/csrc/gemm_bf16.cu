@@ -140,7 +140,11 @@ conv_gemm_bf16_kernel(FclConvGemmBf16Params p, int stages) {
               const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)grow * p.ldr + n0 + c0 + col));
               o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
             }
-            *reinterpret_cast<float4*>(p.out + (size_t)grow * p.ldo + n0 + c0 + col) = o;
+            if (p.out_bf16)
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)grow * p.ldo + n0 + c0 + col) =
+                  make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+            else
+              *reinterpret_cast<float4*>(p.out + (size_t)grow * p.ldo + n0 + c0 + col) = o;
           }
         }
       }

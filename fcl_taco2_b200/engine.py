@@ -58,6 +58,9 @@ class Engine:
                        if bf16_gemms is None or k in bf16_gemms}
             self.bf16_decoder = bf16_decoder
             self.dec_stream = _pack.pack_decoder_stream(packed, hp).to(self.device)
+            self.blstm_whh_bf16 = None
+            if "blstm_wih" in self.wb and (4 * (hp.eunits // 2)) % 256 == 0:
+                self.blstm_whh_bf16 = _pack.pack_bilstm_whh_bf16(packed).to(self.device)
             self.n_slots = _lib.load().fcl_sm_count()
             act_b, c_f = _lib.decoder_bf16_workspace(hp.prenet_units, hp.dunits)
             self.dec_act_ws = torch.empty((self.n_slots * act_b,), dtype=torch.uint8, device=self.device)
@@ -75,7 +78,7 @@ class Engine:
         self.launches += 1
 
     def conv_gemm(self, a, w, bias, rows, cin, cout, taps, act, seg=None, gather=None, residual=None, out=None,
-                  lda=None, key=None, row_gather=None):
+                  lda=None, key=None, row_gather=None, out_bf16=False):
         if out is None:
             out = torch.empty((rows, cout), dtype=torch.float32, device=self.device)
         if key is not None and key in self.wb:
@@ -85,7 +88,7 @@ class Engine:
                                         seg_lo=dptr(seg[0]) if seg else None,
                                         seg_hi=dptr(seg[1]) if seg else None, w_packed=dptr(wp), ntile=ntile,
                                         kstage=kstage, bias=dptr(bias), residual=dptr(residual), ldr=cout,
-                                        out=dptr(out), ldo=cout, act=act)
+                                        out=dptr(out), ldo=cout, act=act, out_bf16=1 if out_bf16 else 0)
             self._call("fcl_conv_gemm_bf16", p)
             return out
         p = _lib.ConvGemmParams(rows=rows, cin=cin, cout=cout, taps=taps, a=dptr(a), lda=lda or cin,
@@ -111,8 +114,18 @@ class Engine:
                            key="enc_conv1")
         x = self.conv_gemm(x, w["enc_conv2_w"], w["enc_conv2_b"], P, hp.econv_chans, hp.econv_chans, 5, ACT_RELU, seg=seg,
                            key="enc_conv2")
-        gx = self.conv_gemm(x, w["blstm_wih"], w["blstm_b"], P, hp.econv_chans, 4 * E, 1, ACT_NONE, key="blstm_wih")
         h = torch.empty((P, E), dtype=torch.float32, device=self.device)
+        if self.precision == "bf16" and getattr(self, "blstm_whh_bf16", None) is not None:
+            gx = torch.empty((P, 4 * E), dtype=torch.bfloat16, device=self.device)
+            self.conv_gemm(x, None, w["blstm_b"], P, hp.econv_chans, 4 * E, 1, ACT_NONE, key="blstm_wih", out=gx,
+                           out_bf16=True)
+            n_tiles = (n_utts + 127) // 128
+            c_ws = torch.empty((n_tiles * 2 * (E // 2) * 128,), dtype=torch.float32, device=self.device)
+            self._call("fcl_bilstm_bf16", _lib.BiLstmBf16Params(n_utts=n_utts, hidden=E // 2, utt_off=dptr(utt_off),
+                                                                gx=dptr(gx), whh_packed=dptr(self.blstm_whh_bf16),
+                                                                c_ws=dptr(c_ws), out=dptr(h)))
+            return h
+        gx = self.conv_gemm(x, w["blstm_wih"], w["blstm_b"], P, hp.econv_chans, 4 * E, 1, ACT_NONE, key="blstm_wih")
         p = _lib.BiLstmParams(n_utts=n_utts, hidden=E // 2, utt_off=dptr(utt_off), gx=dptr(gx), whh=dptr(w["blstm_whh"]),
                               out=dptr(h), group=8 if n_utts >= 8 else 1)
         self._call("fcl_bilstm_f32", p)

@@ -155,3 +155,10 @@ def pack_decoder_stream(packed_fp32: dict, hp) -> torch.Tensor:
         pack_conv_bf16(pc.unsqueeze(0), 256, 64)[0],
     ]
     return torch.cat(parts).contiguous()
+
+
+def pack_bilstm_whh_bf16(packed_fp32: dict) -> torch.Tensor:
+    """W_hh of both directions as bf16 UMMA B stages: [dir][4H/256 chunks][H/64 k-stages][8][256][8]
+    (csrc/bilstm_bf16.cu). Input: packed_fp32["blstm_whh"] (2, H, 4H) gate-interleaved columns."""
+    whh = packed_fp32["blstm_whh"]
+    return torch.cat([pack_conv_bf16(whh[d].unsqueeze(0), 256, 64)[0] for d in range(2)]).contiguous()

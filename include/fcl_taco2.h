@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 7
+#define FCL_ABI_VERSION 8
 
 enum {
   FCL_OK = 0,
@@ -126,6 +126,7 @@ typedef struct {
   float* out;
   int32_t ldo;
   int32_t act;
+  int32_t out_bf16;          /* != 0: `out` is bf16 (rows, ldo) instead of fp32             */
 } FclConvGemmBf16Params;
 int fcl_conv_gemm_bf16(const FclConvGemmBf16Params* p, void* stream);
 
@@ -182,6 +183,22 @@ typedef struct {
   int32_t group;             /* utterances per CTA: 1 or 8                                 */
 } FclBiLstmParams;
 int fcl_bilstm_f32(const FclBiLstmParams* p, void* stream);
+
+/* Tensor-core form (tcgen05): tiles of 128 utterances x direction, h kept on chip as a bf16 operand image,
+ * W_hh streamed through a bulk-copy ring. Utterances should be ordered longest-first (the batch planner does).
+ *   gx         : (P, 2, 4*hidden) bf16, gate-interleaved (fcl_conv_gemm_bf16 with out_bf16 = 1)
+ *   whh_packed : bf16 [dir][4*hidden/256][hidden/64] blocks of [8][256][8] (pack.py: pack_bilstm_whh_bf16)
+ *   c_ws       : scratch, ceil(n_utts/128) * 2 * hidden * 128 floats
+ */
+typedef struct {
+  int32_t n_utts, hidden;
+  const int32_t* utt_off;
+  const void* gx;
+  const void* whh_packed;
+  float* c_ws;
+  float* out;                /* (P, 2*hidden) fp32: [fwd | bwd] */
+} FclBiLstmBf16Params;
+int fcl_bilstm_bf16(const FclBiLstmBf16Params* p, void* stream);
 
 /* ---------------------------------------------------------------- K4: persistent decoder
  * The step loop of nets/modules/decoder_sa.py:577-617 (Prenet :146-158 with its always-on
