@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -36,9 +36,15 @@ class ConvGemmParams(C.Structure):
 
 class ConvGemmBf16Params(C.Structure):
     _fields_ = [("rows", i32), ("cin", i32), ("cout", i32), ("taps", i32), ("a", ptr), ("lda", i32),
-                ("gather", ptr), ("row_gather", ptr), ("seg_lo", ptr), ("seg_hi", ptr), ("w_packed", ptr),
-                ("ntile", i32), ("kstage", i32), ("bias", ptr), ("residual", ptr), ("ldr", i32), ("out", ptr),
-                ("ldo", i32), ("act", i32), ("out_bf16", i32)]
+                ("gather", ptr), ("row_gather", ptr), ("tile_src", ptr), ("tile_dst", ptr), ("n_tiles_dev", ptr),
+                ("n_tiles", i32), ("map_halo", i32), ("w_packed", ptr), ("ntile", i32), ("kstage", i32),
+                ("bias", ptr), ("residual", ptr), ("ldr", i32), ("out", ptr), ("ldo", i32), ("act", i32),
+                ("out_bf16", i32)]
+
+
+class ConvTilesParams(C.Structure):
+    _fields_ = [("n_segs", i32), ("max_tiles", i32), ("halo", i32), ("seg_off", ptr), ("seg_first_tile", ptr),
+                ("tile_src", ptr), ("tile_dst", ptr), ("n_tiles", ptr)]
 
 
 class LayerNormParams(C.Structure):
@@ -82,7 +88,7 @@ class PackRowsParams(C.Structure):
 
 
 STRUCTS = [LenRegParams, FrameMapParams, ConvGemmParams, LayerNormParams, EmbedAddParams, BiLstmParams,
-           DecoderParams, ConvGemmBf16Params, DecoderBf16Params, PackRowsParams, BiLstmBf16Params]
+           DecoderParams, ConvGemmBf16Params, DecoderBf16Params, PackRowsParams, BiLstmBf16Params, ConvTilesParams]
 
 ENTRY_POINTS = {
     "fcl_len_reg_scan": LenRegParams,
@@ -96,6 +102,7 @@ ENTRY_POINTS = {
     "fcl_decoder_bf16": DecoderBf16Params,
     "fcl_pack_rows_bf16": PackRowsParams,
     "fcl_bilstm_bf16": BiLstmBf16Params,
+    "fcl_conv_tiles": ConvTilesParams,
 }
 PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_last_error", "fcl_sm_count", "fcl_struct_size",
                  "fcl_decoder_bf16_workspace"]

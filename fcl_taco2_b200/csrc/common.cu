@@ -47,6 +47,7 @@ extern "C" int fcl_struct_size(int which) {
     case 8: return (int)sizeof(FclDecoderBf16Params);
     case 9: return (int)sizeof(FclPackRowsParams);
     case 10: return (int)sizeof(FclBiLstmBf16Params);
+    case 11: return (int)sizeof(FclConvTilesParams);
     default: return -1;
   }
 }

@@ -83,10 +83,14 @@ class Engine:
             out = torch.empty((rows, cout), dtype=torch.float32, device=self.device)
         if key is not None and key in self.wb:
             wp, ntile, kstage = self.wb[key]
+            tm = seg[2] if (seg is not None and taps > 1) else None      # tile maps of the row space
             p = _lib.ConvGemmBf16Params(rows=rows, cin=cin, cout=cout, taps=taps, a=dptr(a), lda=lda or cin,
                                         gather=dptr(gather), row_gather=dptr(row_gather),
-                                        seg_lo=dptr(seg[0]) if seg else None,
-                                        seg_hi=dptr(seg[1]) if seg else None, w_packed=dptr(wp), ntile=ntile,
+                                        tile_src=dptr(tm["src"]) if tm else None,
+                                        tile_dst=dptr(tm["dst"]) if tm else None,
+                                        n_tiles_dev=dptr(tm["count"]) if tm else None,
+                                        n_tiles=tm["max_tiles"] if tm else 0, map_halo=tm["halo"] if tm else 0,
+                                        w_packed=dptr(wp), ntile=ntile,
                                         kstage=kstage, bias=dptr(bias), residual=dptr(residual), ldr=cout,
                                         out=dptr(out), ldo=cout, act=act, out_bf16=1 if out_bf16 else 0)
             self._call("fcl_conv_gemm_bf16", p)
@@ -97,6 +101,20 @@ class Engine:
                                 residual=dptr(residual), ldr=cout, out=dptr(out), ldo=cout, act=act)
         self._call("fcl_conv_gemm_f32", p)
         return out
+
+    def conv_tiles(self, seg_off, n_segs, max_tiles, halo=2):
+        """Tile maps of a ragged row space for the tensor-core convolutions (None on the fp32 path)."""
+        if self.precision != "bf16":
+            return None
+        dev = self.device
+        first = torch.empty((n_segs + 1,), dtype=torch.int32, device=dev)
+        src = torch.empty((max_tiles, 136), dtype=torch.int32, device=dev)
+        dst = torch.empty((max_tiles, 128), dtype=torch.int32, device=dev)
+        count = torch.empty((1,), dtype=torch.int32, device=dev)
+        self._call("fcl_conv_tiles", _lib.ConvTilesParams(n_segs=n_segs, max_tiles=max_tiles, halo=halo,
+                                                          seg_off=dptr(seg_off), seg_first_tile=dptr(first),
+                                                          tile_src=dptr(src), tile_dst=dptr(dst), n_tiles=dptr(count)))
+        return {"src": src, "dst": dst, "count": count, "max_tiles": max_tiles, "halo": halo, "first": first}
 
     def layernorm(self, x, g, b, y=None, head_w=None, head_b=0.0, head_out=None, dur_out=None):
         rows, chans = x.shape
@@ -295,9 +313,10 @@ class Engine:
         """The pass proper, inputs already resident on the device (`d` from `upload`)."""
         hp = self.hp
         B, P = plan.n_utts, plan.n_rows
-        seg = (d["seg_lo"], d["seg_hi"])
         ex = {"h2d_bytes": h2d}
+        lens = np.diff(plan.utt_off.astype(np.int64))
         with self.stage("encoder"):
+            seg = (d["seg_lo"], d["seg_hi"], self.conv_tiles(d["utt_off"], B, int(((lens + 127) // 128).sum())))
             h = self.encoder(d["ids"], d["utt_off"], seg, B)
         need_pred_dur = plan.dur is None
         dlog = dur_pred = None
@@ -330,8 +349,9 @@ class Engine:
                               dropout_seed, tile_rows)
         with self.stage("frame_map"):
             fmap, pos = self.frame_map(frame_off, utt_frame_off, P, B, F, want_position=extras)
+            ftiles = self.conv_tiles(utt_frame_off, B, (F + 127) // 128 + B)
         with self.stage("postnet"):
-            out = self.postnet(before, (fmap[2], fmap[3]), F)
+            out = self.postnet(before, (fmap[2], fmap[3], ftiles), F)
         if extras:
             ex.update(h=h, dlog=dlog, dur_pred=dur_pred, pitch=pitch, energy=energy, hn=hn, before=before,
                       frame_off=frame_off, order=order, frame_row=fmap[0], frame_step=fmap[1], position=pos,

@@ -102,7 +102,7 @@ def choose_kstage(cin: int) -> int:
 
 
 def pack_conv_bf16(w: torch.Tensor, ntile: int | None = None, kstage: int | None = None):
-    """(taps, cin, cout) fp32 -> bf16 blocks [cout/ntile][taps*cin/kstage][kstage/8][ntile][8]
+    """(taps, cin, cout) fp32 -> bf16 blocks [cout/ntile][cin/kstage][taps][kstage/8][ntile][8]
     (UMMA K-major no-swizzle core-matrix image of each (ntile x kstage) B stage; csrc/umma.cuh).
     -> (flat bf16 tensor, ntile, kstage)"""
     taps, cin, cout = w.shape
@@ -110,7 +110,7 @@ def pack_conv_bf16(w: torch.Tensor, ntile: int | None = None, kstage: int | None
     kstage = kstage or choose_kstage(cin)
     assert cout % ntile == 0 and cin % kstage == 0 and kstage % 16 == 0
     x = w.reshape(taps, cin // kstage, kstage // 8, 8, cout // ntile, ntile)      # t, kc, k8, j, nt, n
-    x = x.permute(4, 0, 1, 2, 5, 3).contiguous()                                   # nt, t, kc, k8, n, j
+    x = x.permute(4, 1, 0, 2, 5, 3).contiguous()                                   # nt, kc, t, k8, n, j
     return x.to(torch.bfloat16).reshape(-1).contiguous(), ntile, kstage
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 8
+#define FCL_ABI_VERSION 9
 
 enum {
   FCL_OK = 0,
@@ -106,17 +106,33 @@ int fcl_conv_gemm_f32(const FclConvGemmParams* p, void* stream);
 
 /* Tensor-core form of the same contract (tcgen05, bf16 operands, fp32 accumulate in TMEM, fp32 activations
  * in HBM). `w_packed` holds bf16 weights pre-tiled as UMMA core matrices:
- *   [cout/ntile][taps*cin/kstage][kstage/8][ntile][8]   (see fcl_taco2_b200/pack.py: pack_conv_bf16)
- * so that one pipeline stage of the B operand is one contiguous bulk copy.
+ *   [cout/ntile][cin/kstage][taps][kstage/8][ntile][8]   (see fcl_taco2_b200/pack.py: pack_conv_bf16)
+ * so that one weight stage is one contiguous bulk copy. For taps > 1 the row tiles come from fcl_conv_tiles
+ * (a tile never crosses an utterance; its input window is fetched once and the taps are descriptor shifts).
  */
+typedef struct {
+  int32_t n_segs;                 /* utterances                                              */
+  int32_t max_tiles;              /* capacity of the maps: >= sum over segments of ceil(len/128) */
+  int32_t halo;                   /* window halo rows on each side (>= taps/2 of every conv using the maps, <= 4) */
+  const int32_t* seg_off;         /* (n_segs+1) row offsets of the segments                  */
+  int32_t* seg_first_tile;        /* out (n_segs+1) scratch: first tile of each segment      */
+  int32_t* tile_src;              /* out (max_tiles, 136): global row of each window row, -1 = zero */
+  int32_t* tile_dst;              /* out (max_tiles, 128): global row of each output row, -1 = none */
+  int32_t* n_tiles;               /* out (1): number of tiles                                */
+} FclConvTilesParams;
+int fcl_conv_tiles(const FclConvTilesParams* p, void* stream);
+
 typedef struct {
   int32_t rows, cin, cout, taps;
   const float* a;
   int32_t lda;
   const int64_t* gather;     /* optional: A row r is table row gather[r] (embedding ids)   */
   const int32_t* row_gather; /* optional: A row r is row row_gather[r] of `a` (row permutation) */
-  const int32_t* seg_lo;
-  const int32_t* seg_hi;
+  const int32_t* tile_src;   /* tile maps (fcl_conv_tiles); NULL => plain 128-row tiles (taps must be 1) */
+  const int32_t* tile_dst;
+  const int32_t* n_tiles_dev;/* optional device count of valid tiles (grid = n_tiles is an upper bound) */
+  int32_t n_tiles;           /* tiles to launch when tile maps are given                   */
+  int32_t map_halo;          /* halo the maps were built with                              */
   const void* w_packed;      /* bf16, layout above                                         */
   int32_t ntile;             /* output columns per CTA: multiple of 16, <= 256, divides cout */
   int32_t kstage;            /* K per pipeline stage: multiple of 16, <= 80, divides cin    */

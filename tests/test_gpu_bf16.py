@@ -69,17 +69,30 @@ def test_conv_gemm_bf16_matches_bf16_rounded_reference(rows, cin, cout, taps, ac
     out = torch.full((rows, cout), float("nan"), device="cuda")
     bias_d = bias.cuda()
     res_d = res.cuda() if use_res else None
+    stream = torch.cuda.current_stream().cuda_stream
+    tsrc = tdst = cnt = None
+    max_tiles = 0
+    if taps > 1:                                      # tile maps: a tile never crosses a segment
+        seg_off = torch.from_numpy(off).cuda()
+        max_tiles = int(sum((n + 127) // 128 for n in seg_lens)) + 3        # + slack: extra CTAs must exit cleanly
+        first = torch.empty(len(seg_lens) + 1, dtype=torch.int32, device="cuda")
+        tsrc = torch.empty((max_tiles, 136), dtype=torch.int32, device="cuda")
+        tdst = torch.empty((max_tiles, 128), dtype=torch.int32, device="cuda")
+        cnt = torch.empty(1, dtype=torch.int32, device="cuda")
+        _lib.call("fcl_conv_tiles", _lib.ConvTilesParams(n_segs=len(seg_lens), max_tiles=max_tiles, halo=2,
+                                                         seg_off=dptr(seg_off), seg_first_tile=dptr(first),
+                                                         tile_src=dptr(tsrc), tile_dst=dptr(tdst), n_tiles=dptr(cnt)), stream)
     p = _lib.ConvGemmBf16Params(rows=rows, cin=cin, cout=cout, taps=taps, a=dptr(a_dev), lda=cin, gather=dptr(gather),
-                                seg_lo=dptr(lo) if taps > 1 else None, seg_hi=dptr(hi) if taps > 1 else None,
-                                w_packed=dptr(wp), ntile=ntile, kstage=kstage, bias=dptr(bias_d), residual=dptr(res_d),
-                                ldr=cout, out=dptr(out), ldo=cout, act=act)
-    _lib.call("fcl_conv_gemm_bf16", p, torch.cuda.current_stream().cuda_stream)
+                                tile_src=dptr(tsrc), tile_dst=dptr(tdst), n_tiles_dev=dptr(cnt), n_tiles=max_tiles,
+                                map_halo=2, w_packed=dptr(wp), ntile=ntile, kstage=kstage, bias=dptr(bias_d),
+                                residual=dptr(res_d), ldr=cout, out=dptr(out), ldo=cout, act=act)
+    _lib.call("fcl_conv_gemm_bf16", p, stream)
     torch.cuda.synchronize()
     ref = _ref_conv(a_ref, w, bias, seg_lens if taps > 1 else [rows], taps, act, res)
     got = out.cpu()
     assert torch.isfinite(got).all()
     err = float((got - ref).abs().max())
-    assert err < 2e-3 * max(1.0, float(ref.abs().max())), err
+    assert err < 3e-3 * max(1.0, float(ref.abs().max())), err     # tanh.approx in the epilogue: ~1e-3
 
 
 # ----------------------------------------------------------------------------- decoder / end-to-end, bf16 path
