@@ -151,7 +151,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="S", choices=["S", "T"])
     ap.add_argument("--batch", type=int, default=1024)
-    ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--stress", action="store_true")
     ap.add_argument("--latency-utts", type=int, default=200)
