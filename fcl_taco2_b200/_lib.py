@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 9
+ABI_VERSION = 11
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -47,6 +47,23 @@ class ConvTilesParams(C.Structure):
                 ("tile_src", ptr), ("tile_dst", ptr), ("n_tiles", ptr)]
 
 
+MAX_STACK_LAYERS = 5
+
+
+class ConvLayer(C.Structure):
+    _fields_ = [("cin", i32), ("cout", i32), ("kstage", i32), ("act", i32), ("w_packed", ptr), ("bias", ptr)]
+
+
+class ConvStackTilesParams(C.Structure):
+    _fields_ = [("n_segs", i32), ("max_tiles", i32), ("stride", i32), ("seg_off", ptr), ("tiles", ptr), ("n_tiles", ptr)]
+
+
+class ConvStackParams(C.Structure):
+    _fields_ = [("n_layers", i32), ("taps", i32), ("layers", ConvLayer * MAX_STACK_LAYERS), ("in_", ptr), ("ld_in", i32),
+                ("gather", ptr), ("tiles", ptr), ("n_tiles_dev", ptr), ("n_tiles", i32), ("residual", ptr),
+                ("ldr", i32), ("out", ptr), ("ldo", i32)]
+
+
 class LayerNormParams(C.Structure):
     _fields_ = [("rows", i32), ("chans", i32), ("x", ptr), ("gamma", ptr), ("beta", ptr), ("y", ptr),
                 ("head_w", ptr), ("head_b", f32), ("head_out", ptr), ("dur_out", ptr)]
@@ -75,12 +92,18 @@ class DecoderBf16Params(C.Structure):
                 ("prenet_units", i32), ("odim", i32), ("order", ptr), ("dur", ptr), ("frame_off", ptr),
                 ("row_utt", ptr), ("row_phone", ptr), ("hn_img", ptr), ("w_stream", ptr), ("bp0", ptr), ("bp1", ptr),
                 ("wpos", ptr), ("b0", ptr), ("b1", ptr), ("act_ws", ptr), ("c_ws", ptr), ("before", ptr),
-                ("zoneout", f32), ("dropout_p", f32), ("dropout_seed", u64), ("trace", ptr), ("trace_cap", i32)]
+                ("zoneout", f32), ("dropout_p", f32), ("dropout_seed", u64), ("tile_slot", ptr), ("tile_rank", ptr),
+                ("trace", ptr), ("trace_cap", i32)]
 
 
 class BiLstmBf16Params(C.Structure):
-    _fields_ = [("n_utts", i32), ("hidden", i32), ("utt_off", ptr), ("gx", ptr), ("whh_packed", ptr), ("c_ws", ptr),
-                ("out", ptr)]
+    _fields_ = [("n_utts", i32), ("hidden", i32), ("tile_utts", i32), ("utt_off", ptr), ("gx", ptr),
+                ("whh_packed", ptr), ("c_ws", ptr), ("out", ptr)]
+
+
+class DecoderScheduleParams(C.Structure):
+    _fields_ = [("n_rows", i32), ("n_tiles", i32), ("n_slots", i32), ("order", ptr), ("dur", ptr),
+                ("tile_slot", ptr), ("tile_rank", ptr)]
 
 
 class PackRowsParams(C.Structure):
@@ -88,7 +111,8 @@ class PackRowsParams(C.Structure):
 
 
 STRUCTS = [LenRegParams, FrameMapParams, ConvGemmParams, LayerNormParams, EmbedAddParams, BiLstmParams,
-           DecoderParams, ConvGemmBf16Params, DecoderBf16Params, PackRowsParams, BiLstmBf16Params, ConvTilesParams]
+           DecoderParams, ConvGemmBf16Params, DecoderBf16Params, PackRowsParams, BiLstmBf16Params, ConvTilesParams, DecoderScheduleParams, ConvStackTilesParams,
+           ConvStackParams]
 
 ENTRY_POINTS = {
     "fcl_len_reg_scan": LenRegParams,
@@ -103,6 +127,9 @@ ENTRY_POINTS = {
     "fcl_pack_rows_bf16": PackRowsParams,
     "fcl_bilstm_bf16": BiLstmBf16Params,
     "fcl_conv_tiles": ConvTilesParams,
+    "fcl_decoder_schedule": DecoderScheduleParams,
+    "fcl_conv_stack_tiles": ConvStackTilesParams,
+    "fcl_conv_stack_bf16": ConvStackParams,
 }
 PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_last_error", "fcl_sm_count", "fcl_struct_size",
                  "fcl_decoder_bf16_workspace"]

@@ -41,11 +41,12 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
   const uint32_t himg_bytes = (uint32_t)H * 256u;         // [H/8][128][8] bf16
   uint8_t* himg = smem + (size_t)stages * kBlBBytes;       // two h images after the ring
 
-  const int u_first = tile * 128;
+  const int R = p.tile_utts;                              // utterances per tile (rows >= R stay idle)
+  const int u_first = tile * R;
   __shared__ int s_steps;
   if (tid == 0) s_steps = 0;
   __syncthreads();
-  if (tid < 128 && u_first + tid < p.n_utts) atomicMax(&s_steps, p.utt_off[u_first + tid + 1] - p.utt_off[u_first + tid]);
+  if (tid < R && u_first + tid < p.n_utts) atomicMax(&s_steps, p.utt_off[u_first + tid + 1] - p.utt_off[u_first + tid]);
   __syncthreads();
   const int steps = s_steps;                             // longest utterance of the tile
 
@@ -117,7 +118,7 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     const int u = u_first + r;
     int off = 0, len = 0;
-    if (u < p.n_utts) { off = p.utt_off[u]; len = p.utt_off[u + 1] - off; }
+    if (r < R && u < p.n_utts) { off = p.utt_off[u]; len = p.utt_off[u + 1] - off; }
     float* cst = p.c_ws + ((size_t)(tile * 2 + dir) * H) * 128;        // [H][128]
     const size_t gx_ld = (size_t)8 * H;                                // bf16 elements per gx row
     uint32_t chunk_ctr = 0;
@@ -214,7 +215,8 @@ extern "C" int fcl_bilstm_bf16(const FclBiLstmBf16Params* p, void* stream) {
     if (e != cudaSuccess) { set_error("fcl_bilstm_bf16: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
     attr_smem = smem;
   }
-  dim3 grid((p->n_utts + 127) / 128, 2);
+  FCL_REQUIRE(p->tile_utts == 32 || p->tile_utts == 64 || p->tile_utts == 128, "tile_utts must be 32, 64 or 128");
+  dim3 grid((p->n_utts + p->tile_utts - 1) / p->tile_utts, 2);
   bilstm_bf16_kernel<<<grid, kBlThreads, smem, as_stream(stream)>>>(*p, stages);
   return check_launch("fcl_bilstm_bf16");
 }

@@ -48,6 +48,9 @@ extern "C" int fcl_struct_size(int which) {
     case 9: return (int)sizeof(FclPackRowsParams);
     case 10: return (int)sizeof(FclBiLstmBf16Params);
     case 11: return (int)sizeof(FclConvTilesParams);
+    case 12: return (int)sizeof(FclDecoderScheduleParams);
+    case 13: return (int)sizeof(FclConvStackTilesParams);
+    case 14: return (int)sizeof(FclConvStackParams);
     default: return -1;
   }
 }

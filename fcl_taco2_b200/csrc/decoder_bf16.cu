@@ -37,12 +37,15 @@ constexpr uint32_t kABytes = 128u * 64u * 2u;           // one A stage: 128 rows
 constexpr uint32_t kBBytesMax = 256u * 64u * 2u;        // one B stage: up to 256 cols x 64 k
 constexpr uint32_t kStageBytes = kABytes + kBBytesMax;  // 48 KB
 constexpr int kEpiThreads = 512;
+constexpr int kDbMaxTilesPerCta = 512;
 
 struct DbShared {
   uint64_t full[kDbStages], empty[kDbStages];
   uint64_t tmem_full[2], tmem_empty[2];
   uint64_t a_ready[4];        // x1, x2, z0', z1' operand images complete (epilogue -> producer)
   uint32_t tmem_base;
+  int n_my_tiles;
+  int my_tiles[kDbMaxTilesPerCta];
 };
 
 // activation scratch of one CTA slot (bytes): x1 | x2 | z0a z0b z1a z1b
@@ -53,14 +56,8 @@ __host__ __device__ inline size_t db_z_off(int U, int H, int which /*0..3: z0a z
 }
 __host__ __device__ inline size_t db_act_bytes(int U, int H) { return db_z_off(U, H, 4); }
 
-// tile visited at round `tk` by this CTA: boustrophedon over duration-sorted tiles (longest first), so every
-// CTA gets a similar sum of steps. < 0 when done.
-__device__ __forceinline__ int db_tile(int tk, int n_tiles) {
-  const int G = gridDim.x, b = blockIdx.x;
-  const int t = tk * G + ((tk & 1) ? (G - 1 - b) : b);
-  if (tk * G >= n_tiles) return -1;
-  return t < n_tiles ? t : -2;          // -2: no tile for this CTA in the last, partial round
-}
+// tile visited at round `tk` by this CTA: from the LPT schedule (fcl_decoder_schedule) staged in shared memory.
+#define DB_TILE(tk) ((tk) < sh.n_my_tiles ? sh.my_tiles[tk] : -1)
 
 // optional timeline trace of CTA 0 (debug/profiling aid; p.trace == nullptr in production).
 // record = {event id, clock64}; ids: 100+phase*10+chunk (MMA: accumulator free), 200+.. (MMA: first stage landed),
@@ -128,6 +125,15 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
   uint8_t* act = reinterpret_cast<uint8_t*>(p.act_ws) + (size_t)blockIdx.x * db_act_bytes(U, H);
   float* cws = p.c_ws + (size_t)blockIdx.x * 2 * H * 128;
 
+  // this CTA's tile list (longest-processing-time schedule)
+  if (tid == 0) sh.n_my_tiles = 0;
+  __syncthreads();
+  for (int t = tid; t < p.n_tiles; t += kDbThreads) {
+    if (p.tile_slot[t] == (int)blockIdx.x) {
+      const int k = p.tile_rank[t];
+      if (k < kDbMaxTilesPerCta) { sh.my_tiles[k] = t; atomicMax(&sh.n_my_tiles, k + 1); }
+    }
+  }
   if (tid == 0) {
     for (int s = 0; s < kDbStages; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&sh.tmem_full[b], 1); mbar_init(&sh.tmem_empty[b], kEpiThreads); }
@@ -146,7 +152,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
     if (elect_one()) {
       uint32_t stage = 0, sphase = 0;                 // ring position / parity
       uint32_t rdy[4] = {0, 0, 0, 0};                 // parity of each a_ready barrier
-      for (int tk = 0, tile; (tile = db_tile(tk, p.n_tiles)) >= 0; ++tk) {
+      for (int tk = 0, tile; (tile = DB_TILE(tk)) >= 0; ++tk) {
         const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
         const uint8_t* himg = reinterpret_cast<const uint8_t*>(p.hn_img) + (size_t)tile * E * 128 * 2;
         for (int m = 0; m < steps; ++m) {
@@ -191,7 +197,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
       uint32_t stage = 0, sphase = 0;
       uint32_t chunk_ctr = 0;                          // accumulator buffer = chunk_ctr & 1
       const uint32_t idesc_wide = idesc_bf16_f32(128u, 256u), idesc_feat = idesc_bf16_f32(128u, (uint32_t)O);
-      for (int tk = 0, tile; (tile = db_tile(tk, p.n_tiles)) >= 0; ++tk) {
+      for (int tk = 0, tile; (tile = DB_TILE(tk)) >= 0; ++tk) {
         const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
         for (int m = 0; m < steps; ++m) {
           for (int phase = 0; phase < 4; ++phase) {
@@ -241,7 +247,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
     const uint32_t drop_thr = dropout_threshold16(p.dropout_p);
     const float drop_scale = use_drop ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
 
-    for (int tk = 0, tile; (tile = db_tile(tk, p.n_tiles)) >= 0; ++tk) {
+    for (int tk = 0, tile; (tile = DB_TILE(tk)) >= 0; ++tk) {
       const int sidx = tile * 128 + r;
       int row = -1, d = 0, foff = 0, utt = 0, ph = 0;
       if (sidx < p.n_rows) {
@@ -422,6 +428,50 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
 
 }  // namespace fcl
 
+namespace fcl {
+// LPT: tiles are duration-descending; each goes to the currently least-loaded slot (ties -> lowest slot).
+__global__ void __launch_bounds__(256, 1)
+decoder_schedule_kernel(FclDecoderScheduleParams p) {
+  extern __shared__ int s_steps[];                    // steps of every tile, loaded in parallel first
+  for (int t = threadIdx.x; t < p.n_tiles; t += blockDim.x)
+    s_steps[t] = min(max(p.dur[p.order[(size_t)t * 128]], 0), FCL_MAX_DURATION);
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  constexpr int kPerLane = 8;                         // up to 256 slots
+  const int lane = threadIdx.x;
+  int load[kPerLane], cnt[kPerLane];
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) { load[i] = (lane + 32 * i) < p.n_slots ? 0 : 0x7fffffff; cnt[i] = 0; }
+  for (int t = 0; t < p.n_tiles; ++t) {
+    const int steps = s_steps[t];
+    int best = load[0], bslot = lane;
+#pragma unroll
+    for (int i = 1; i < kPerLane; ++i) if (load[i] < best) { best = load[i]; bslot = lane + 32 * i; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, bslot, o);
+      if (ob < best || (ob == best && os < bslot)) { best = ob; bslot = os; }
+    }
+    int rank = 0;
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+      if (bslot == lane + 32 * i) { load[i] += steps + 1; rank = cnt[i]; cnt[i] += 1; }
+    }
+    rank = __shfl_sync(0xffffffffu, rank, bslot & 31);
+    if (lane == 0) { p.tile_slot[t] = bslot; p.tile_rank[t] = rank; }
+  }
+}
+}  // namespace fcl
+
+extern "C" int fcl_decoder_schedule(const FclDecoderScheduleParams* p, void* stream) {
+  using namespace fcl;
+  FCL_REQUIRE(p && p->order && p->dur && p->tile_slot && p->tile_rank, "null pointer");
+  FCL_REQUIRE(p->n_rows > 0 && p->n_tiles == (p->n_rows + 127) / 128 && p->n_slots >= 1 && p->n_slots <= 256, "bad sizes");
+  FCL_REQUIRE(p->n_tiles <= 12000, "too many tiles for the single-CTA scheduler");
+  decoder_schedule_kernel<<<1, 256, (size_t)p->n_tiles * sizeof(int), as_stream(stream)>>>(*p);
+  return check_launch("fcl_decoder_schedule");
+}
+
 extern "C" int fcl_decoder_bf16_workspace(int32_t prenet_units, int32_t dunits, int64_t* act_bytes_per_slot,
                                           int64_t* c_floats_per_slot) {
   if (!act_bytes_per_slot || !c_floats_per_slot) return FCL_EINVAL;
@@ -433,8 +483,10 @@ extern "C" int fcl_decoder_bf16_workspace(int32_t prenet_units, int32_t dunits, 
 extern "C" int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream) {
   using namespace fcl;
   FCL_REQUIRE(p && p->order && p->dur && p->frame_off && p->row_utt && p->row_phone && p->hn_img &&
-                  p->w_stream && p->bp0 && p->bp1 && p->wpos && p->b0 && p->b1 && p->act_ws && p->c_ws && p->before,
+                  p->w_stream && p->bp0 && p->bp1 && p->wpos && p->b0 && p->b1 && p->act_ws && p->c_ws && p->before &&
+                  p->tile_slot && p->tile_rank,
               "null pointer");
+  FCL_REQUIRE((long long)p->n_tiles <= (long long)kDbMaxTilesPerCta * p->n_slots, "too many tiles for the per-CTA tile list");
   FCL_REQUIRE(p->eunits % 64 == 0 && p->eunits >= 64, "eunits must be a multiple of 64");
   FCL_REQUIRE(p->n_rows > 0 && p->n_tiles == (p->n_rows + 127) / 128, "n_tiles must be ceil(n_rows / 128)");
   FCL_REQUIRE(p->prenet_units == 256, "prenet_units must be 256 (one 256-column chunk)");

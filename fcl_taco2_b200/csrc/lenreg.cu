@@ -49,11 +49,15 @@ len_reg_scan_kernel(FclLenRegParams p) {
   const int chunk = (P + kScanThreads - 1) / kScanThreads;
   const int lo = min(tid * chunk, P), hi = min(lo + chunk, P);
   int sum = 0, mx = 0;
-  for (int r = lo; r < hi; ++r) {
-    int d = min(max(p.dur[r], 0), FCL_MAX_DURATION);
-    sum += d;
+  for (int k = 0; k < chunk; ++k) {                    // warp-uniform trip count: match_any needs converged lanes
+    const int r = lo + k;
+    const bool ok = r < hi;
+    const int d = ok ? min(max(p.dur[r], 0), FCL_MAX_DURATION) : -1;
+    sum += ok ? d : 0;
     mx = max(mx, d);
-    atomicAdd(&hist[d], 1);
+    // warp-aggregated histogram update: one shared-memory atomic per distinct duration in the warp
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (ok && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[d], __popc(peers));
   }
   atomicMax(&maxd_s, mx);
   int excl = block_excl_scan(sum, warp_sums, &total_s);
@@ -79,10 +83,16 @@ len_reg_scan_kernel(FclLenRegParams p) {
   int start = block_excl_scan(cnt, warp_sums, &total_s);
   hist[mybin] = start;                 // now a cursor
   __syncthreads();
-  for (int r = lo; r < hi; ++r) {
-    int d = min(max(p.dur[r], 0), FCL_MAX_DURATION);
-    int pos = atomicAdd(&hist[d], 1);
-    p.order[pos] = r;
+  for (int k = 0; k < chunk; ++k) {
+    const int r = lo + k;
+    const bool ok = r < hi;
+    const int d = ok ? min(max(p.dur[r], 0), FCL_MAX_DURATION) : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    int base = 0;
+    if (ok && leader == lane) base = atomicAdd(&hist[d], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (ok) p.order[base + __popc(peers & ((1u << lane) - 1u))] = r;
   }
 }
 

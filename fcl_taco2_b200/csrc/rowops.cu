@@ -81,7 +81,16 @@ layernorm_kernel(FclLayerNormParams p) {
 
 __global__ void __launch_bounds__(256)
 embed_add_kernel(FclEmbedAddParams p) {
-  // one thread per (row, 4 channels)
+  // weights staged in shared memory as [tap][chan] (both embeds), one thread per (row, 4 channels)
+  extern __shared__ __align__(16) float sw[];
+  float* swp = sw;
+  float* swe = sw + (size_t)p.taps * p.chans;
+  for (int i = threadIdx.x; i < p.taps * p.chans; i += blockDim.x) {
+    const int j = i / p.chans, c = i - j * p.chans;
+    swp[i] = p.wp[(size_t)c * p.taps + j];
+    swe[i] = p.we[(size_t)c * p.taps + j];
+  }
+  __syncthreads();
   const int c4 = p.chans >> 2;
   const size_t total = (size_t)p.rows * c4;
   const int half = p.taps >> 1;
@@ -89,24 +98,23 @@ embed_add_kernel(FclEmbedAddParams p) {
     const int r = (int)(i / c4), c = (int)(i - (size_t)r * c4) * 4;
     const int lo = p.seg_lo[r], hi = p.seg_hi[r];
     float4 acc = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)r * p.chans + c));
-    float ap[4] = {0.f, 0.f, 0.f, 0.f}, ae[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 ap = make_float4(0.f, 0.f, 0.f, 0.f), ae = ap;
     for (int j = 0; j < p.taps; ++j) {
       const int src = r + j - half;
       if (src < lo || src >= hi) continue;
       const float pv = __ldg(p.pitch + src), ev = __ldg(p.energy + src);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        ap[k] = fmaf(__ldg(p.wp + (size_t)(c + k) * p.taps + j), pv, ap[k]);
-        ae[k] = fmaf(__ldg(p.we + (size_t)(c + k) * p.taps + j), ev, ae[k]);
-      }
+      const float4 wpv = *reinterpret_cast<const float4*>(swp + (size_t)j * p.chans + c);
+      const float4 wev = *reinterpret_cast<const float4*>(swe + (size_t)j * p.chans + c);
+      ap.x = fmaf(wpv.x, pv, ap.x); ap.y = fmaf(wpv.y, pv, ap.y); ap.z = fmaf(wpv.z, pv, ap.z); ap.w = fmaf(wpv.w, pv, ap.w);
+      ae.x = fmaf(wev.x, ev, ae.x); ae.y = fmaf(wev.y, ev, ae.y); ae.z = fmaf(wev.z, ev, ae.z); ae.w = fmaf(wev.w, ev, ae.w);
     }
     const float4 bp = __ldg(reinterpret_cast<const float4*>(p.bp + c));
     const float4 be = __ldg(reinterpret_cast<const float4*>(p.be + c));
     // same association as the reference: (h + p_emb) + e_emb, embeds carry their bias
-    acc.x = (acc.x + (ap[0] + bp.x)) + (ae[0] + be.x);
-    acc.y = (acc.y + (ap[1] + bp.y)) + (ae[1] + be.y);
-    acc.z = (acc.z + (ap[2] + bp.z)) + (ae[2] + be.z);
-    acc.w = (acc.w + (ap[3] + bp.w)) + (ae[3] + be.w);
+    acc.x = (acc.x + (ap.x + bp.x)) + (ae.x + be.x);
+    acc.y = (acc.y + (ap.y + bp.y)) + (ae.y + be.y);
+    acc.z = (acc.z + (ap.z + bp.z)) + (ae.z + be.z);
+    acc.w = (acc.w + (ap.w + bp.w)) + (ae.w + be.w);
     *reinterpret_cast<float4*>(p.hn + (size_t)r * p.chans + c) = acc;
   }
 }
@@ -169,6 +177,9 @@ extern "C" int fcl_embed_add_f32(const FclEmbedAddParams* p, void* stream) {
   if (sms < 0) return sms;
   size_t total = (size_t)p->rows * (p->chans / 4);
   int blocks = (int)min((total + 255) / 256, (size_t)sms * 8);
-  embed_add_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*p);
+  const size_t smem = (size_t)2 * p->taps * p->chans * sizeof(float);
+  FCL_REQUIRE(smem <= 48 * 1024, "embed weights do not fit the static shared-memory window");
+  blocks = min(blocks, sms * 4);
+  embed_add_kernel<<<blocks, 256, smem, as_stream(stream)>>>(*p);
   return check_launch("fcl_embed_add_f32");
 }

@@ -137,9 +137,11 @@ class Engine:
             gx = torch.empty((P, 4 * E), dtype=torch.bfloat16, device=self.device)
             self.conv_gemm(x, None, w["blstm_b"], P, hp.econv_chans, 4 * E, 1, ACT_NONE, key="blstm_wih", out=gx,
                            out_bf16=True)
-            n_tiles = (n_utts + 127) // 128
+            tile_utts = 32 if n_utts <= 32 * self.n_slots // 2 else 64 if n_utts <= 64 * self.n_slots // 2 else 128
+            n_tiles = (n_utts + tile_utts - 1) // tile_utts
             c_ws = torch.empty((n_tiles * 2 * (E // 2) * 128,), dtype=torch.float32, device=self.device)
-            self._call("fcl_bilstm_bf16", _lib.BiLstmBf16Params(n_utts=n_utts, hidden=E // 2, utt_off=dptr(utt_off),
+            self._call("fcl_bilstm_bf16", _lib.BiLstmBf16Params(n_utts=n_utts, hidden=E // 2, tile_utts=tile_utts,
+                                                                utt_off=dptr(utt_off),
                                                                 gx=dptr(gx), whh_packed=dptr(self.blstm_whh_bf16),
                                                                 c_ws=dptr(c_ws), out=dptr(h)))
             return h
@@ -229,24 +231,69 @@ class Engine:
             hn_img = torch.empty((n_tiles * 128 * E,), dtype=torch.bfloat16, device=self.device)
             self._call("fcl_pack_rows_bf16", _lib.PackRowsParams(n_rows=P, cols=E, src=dptr(hn), ld=E, order=dptr(order),
                                                                  dst=dptr(hn_img)))
+            n_slots = min(self.n_slots, n_tiles)
+            sched = torch.empty((2, n_tiles), dtype=torch.int32, device=self.device)
+            self._call("fcl_decoder_schedule", _lib.DecoderScheduleParams(n_rows=P, n_tiles=n_tiles, n_slots=n_slots,
+                                                                          order=dptr(order), dur=dptr(dur),
+                                                                          tile_slot=dptr(sched[0]), tile_rank=dptr(sched[1])))
         before = torch.empty((max(n_frames, 1), O), dtype=torch.float32, device=self.device)
         trace = getattr(self, "dec_trace", None)
-        p = _lib.DecoderBf16Params(n_rows=P, n_tiles=n_tiles, n_slots=self.n_slots, eunits=E, dunits=H,
+        p = _lib.DecoderBf16Params(n_rows=P, n_tiles=n_tiles, n_slots=n_slots, eunits=E, dunits=H,
                                    prenet_units=hp.prenet_units, odim=O, order=dptr(order), dur=dptr(dur),
                                    frame_off=dptr(frame_off), row_utt=dptr(row_utt), row_phone=dptr(row_phone),
                                    hn_img=dptr(hn_img), w_stream=dptr(self.dec_stream),
                                    bp0=dptr(w["dec_bp0"]), bp1=dptr(w["dec_bp1"]), wpos=dptr(w["dec_wpos"]),
                                    b0=dptr(w["dec_g0h_b"]), b1=dptr(w["dec_b1"]), act_ws=dptr(self.dec_act_ws),
                                    c_ws=dptr(self.dec_c_ws), before=dptr(before), zoneout=zoneout,
-                                   dropout_p=dropout_p, dropout_seed=dropout_seed, trace=dptr(trace),
+                                   dropout_p=dropout_p, dropout_seed=dropout_seed, tile_slot=dptr(sched[0]),
+                                   tile_rank=dptr(sched[1]), trace=dptr(trace),
                                    trace_cap=(trace.numel() - 2) // 2 if trace is not None else 0)
         with self.stage("decoder_loop"):
             self._call("fcl_decoder_bf16", p)
         return before
 
+    def conv_stack(self, keys, acts, x, ld_in, rows, seg_off, n_segs, max_len_sum_tiles, taps=5, gather=None,
+                   residual=None):
+        """Fused conv stack (fcl_conv_stack_bf16) over the layers `keys`; returns None when the stack does not
+        fit on chip (caller falls back to layer-by-layer fcl_conv_gemm_bf16)."""
+        L = len(keys)
+        stride = 128 - 2 * (taps // 2) * (L - 1)
+        layers = (_lib.ConvLayer * _lib.MAX_STACK_LAYERS)()
+        max_c, b_slot = 0, 0
+        for l, key in enumerate(keys):
+            wp, ntile, kstage = self.wb[key]
+            taps_l, cin, cout = self.w[key + "_w"].shape
+            if ntile != cout or taps_l != taps:
+                return None
+            layers[l] = _lib.ConvLayer(cin=cin, cout=cout, kstage=kstage, act=acts[l], w_packed=dptr(wp),
+                                       bias=dptr(self.w[key + "_b"]))
+            max_c, b_slot = max(max_c, cin), max(b_slot, cout * kstage * 2)
+        if 2 * (max_c // 8) * 2176 + 2 * b_slot > 216 * 1024:
+            return None
+        dev = self.device
+        max_tiles = max_len_sum_tiles(stride)
+        tiles = torch.empty((max_tiles, 4), dtype=torch.int32, device=dev)
+        count = torch.empty((1,), dtype=torch.int32, device=dev)
+        self._call("fcl_conv_stack_tiles", _lib.ConvStackTilesParams(n_segs=n_segs, max_tiles=max_tiles, stride=stride,
+                                                                     seg_off=dptr(seg_off), tiles=dptr(tiles),
+                                                                     n_tiles=dptr(count)))
+        cout_last = layers[L - 1].cout
+        out = torch.empty((rows, cout_last), dtype=torch.float32, device=dev)
+        self._call("fcl_conv_stack_bf16", _lib.ConvStackParams(n_layers=L, taps=taps, layers=layers, in_=dptr(x), ld_in=ld_in,
+                                                               gather=dptr(gather), tiles=dptr(tiles), n_tiles_dev=dptr(count),
+                                                               n_tiles=max_tiles, residual=dptr(residual), ldr=cout_last,
+                                                               out=dptr(out), ldo=cout_last))
+        return out
+
     def postnet(self, before, fseg, n_frames):
         hp, w = self.hp, self.w
         O, C = hp.odim, hp.postnet_chans
+        if self.precision == "bf16" and len(fseg) > 3 and all(f"post_conv{l}" in self.wb for l in range(5)):
+            utt_frame_off, n_utts = fseg[3]
+            out = self.conv_stack([f"post_conv{l}" for l in range(5)], [ACT_TANH] * 4 + [ACT_NONE], before, O, n_frames,
+                                  utt_frame_off, n_utts, lambda s: (n_frames + s - 1) // s + n_utts, residual=before)
+            if out is not None:
+                return out
         x = self.conv_gemm(before, w["post_conv0_w"], w["post_conv0_b"], n_frames, O, C, 5, ACT_TANH, seg=fseg,
                            key="post_conv0")
         for l in (1, 2, 3):
@@ -351,7 +398,7 @@ class Engine:
             fmap, pos = self.frame_map(frame_off, utt_frame_off, P, B, F, want_position=extras)
             ftiles = self.conv_tiles(utt_frame_off, B, (F + 127) // 128 + B)
         with self.stage("postnet"):
-            out = self.postnet(before, (fmap[2], fmap[3], ftiles), F)
+            out = self.postnet(before, (fmap[2], fmap[3], ftiles, (utt_frame_off, B)), F)
         if extras:
             ex.update(h=h, dlog=dlog, dur_pred=dur_pred, pitch=pitch, energy=energy, hn=hn, before=before,
                       frame_off=frame_off, order=order, frame_row=fmap[0], frame_step=fmap[1], position=pos,

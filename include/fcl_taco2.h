@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 9
+#define FCL_ABI_VERSION 11
 
 enum {
   FCL_OK = 0,
@@ -146,6 +146,41 @@ typedef struct {
 } FclConvGemmBf16Params;
 int fcl_conv_gemm_bf16(const FclConvGemmBf16Params* p, void* stream);
 
+/* Fused stack of k-tap conv layers (postnet: decoder_sa.py:274-286,632; encoder convs: encoder_sa.py:135-140):
+ * all intermediate activations stay in shared memory as bf16 operand images; only the first input and the last
+ * output touch HBM (halo recompute: a tile yields 128 - 2*(taps/2)*(n_layers-1) output rows).
+ * Every layer: out = act(conv_k(in) + bias) with BatchNorm already folded; the last layer may add `residual`.
+ * Usable when 2 * max(cin)/8 * 2176 B + 2 * max(cout*kstage*2) B fits in shared memory (FCL-taco2-S postnet/encoder).
+ */
+#define FCL_MAX_STACK_LAYERS 5
+typedef struct {
+  int32_t cin, cout, kstage, act;     /* kstage: multiple of 16 (<= 80) dividing cin; act: FCL_ACT_*          */
+  const void* w_packed;               /* bf16 [cin/kstage][taps][kstage/8][cout][8] (pack_conv_bf16, ntile = cout) */
+  const float* bias;                  /* (cout)                                                               */
+} FclConvLayer;
+typedef struct {
+  int32_t n_segs, max_tiles, stride;  /* stride = output rows per tile                                        */
+  const int32_t* seg_off;             /* (n_segs+1)                                                           */
+  int32_t* tiles;                     /* out (max_tiles, 4): first output row, seg_lo, seg_hi, segment        */
+  int32_t* n_tiles;                   /* out (1)                                                              */
+} FclConvStackTilesParams;
+int fcl_conv_stack_tiles(const FclConvStackTilesParams* p, void* stream);
+typedef struct {
+  int32_t n_layers, taps;
+  FclConvLayer layers[FCL_MAX_STACK_LAYERS];
+  const float* in;                    /* (rows, ld_in) fp32, or the embedding table when gather != NULL       */
+  int32_t ld_in;
+  const int64_t* gather;
+  const int32_t* tiles;               /* from fcl_conv_stack_tiles                                            */
+  const int32_t* n_tiles_dev;         /* optional device tile count (grid = n_tiles is an upper bound)        */
+  int32_t n_tiles;
+  const float* residual;              /* optional (rows, ldr), added to the last layer                        */
+  int32_t ldr;
+  float* out;                         /* (rows, ldo)                                                          */
+  int32_t ldo;
+} FclConvStackParams;
+int fcl_conv_stack_bf16(const FclConvStackParams* p, void* stream);
+
 /* ---------------------------------------------------------------- LayerNorm (+ optional head)
  * y = LayerNorm_C(x) * gamma + beta, eps 1e-12 (espnet LayerNorm, variance_predictor.py:62).
  * If head_w != NULL: head[r] = dot(y[r], head_w) + head_b (Linear(C,1), variance_predictor.py:90)
@@ -204,10 +239,12 @@ int fcl_bilstm_f32(const FclBiLstmParams* p, void* stream);
  * W_hh streamed through a bulk-copy ring. Utterances should be ordered longest-first (the batch planner does).
  *   gx         : (P, 2, 4*hidden) bf16, gate-interleaved (fcl_conv_gemm_bf16 with out_bf16 = 1)
  *   whh_packed : bf16 [dir][4*hidden/256][hidden/64] blocks of [8][256][8] (pack.py: pack_bilstm_whh_bf16)
- *   c_ws       : scratch, ceil(n_utts/128) * 2 * hidden * 128 floats
+ *   c_ws       : scratch, ceil(n_utts/tile_utts) * 2 * hidden * 128 floats
+ *   tile_utts  : utterances per CTA tile (32, 64 or 128): the recurrence is a latency/MUFU-bound serial chain,
+ *                so smaller tiles spread it over more SMs (the MMA is M=128 either way)
  */
 typedef struct {
-  int32_t n_utts, hidden;
+  int32_t n_utts, hidden, tile_utts;
   const int32_t* utt_off;
   const void* gx;
   const void* whh_packed;
@@ -294,9 +331,21 @@ typedef struct {
   float zoneout;
   float dropout_p;
   uint64_t dropout_seed;
+  const int32_t* tile_slot;  /* (n_tiles) CTA slot that processes each tile (fcl_decoder_schedule)            */
+  const int32_t* tile_rank;  /* (n_tiles) position of the tile in its slot's list                             */
   int64_t* trace;            /* optional debug timeline of CTA 0: [0] = count (zero it), then (id, clock) pairs */
   int32_t trace_cap;         /* capacity in records                                         */
 } FclDecoderBf16Params;
+/* Longest-processing-time assignment of the duration-sorted tiles to the persistent CTAs (tile cost = its
+ * step count + 1): every CTA ends at about the same time. One warp, ~20 us. */
+typedef struct {
+  int32_t n_rows, n_tiles, n_slots;
+  const int32_t* order;      /* (P) duration-descending row order */
+  const int32_t* dur;        /* (P) */
+  int32_t* tile_slot;        /* out (n_tiles) */
+  int32_t* tile_rank;        /* out (n_tiles) */
+} FclDecoderScheduleParams;
+int fcl_decoder_schedule(const FclDecoderScheduleParams* p, void* stream);
 int fcl_decoder_bf16_workspace(int32_t prenet_units, int32_t dunits, int64_t* act_bytes_per_slot,
                                int64_t* c_floats_per_slot);
 int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream);

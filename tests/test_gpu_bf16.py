@@ -167,3 +167,25 @@ def test_bf16_batched_equals_looped():
     for i in range(len(xs)):
         single = m.inference(torch.from_numpy(xs[i]), None, dur=ds[i], dropout_utt_index=i)
         assert torch.equal(single, outs[i])
+
+
+def test_fused_postnet_stack_matches_layer_by_layer(bf16_engines):
+    """fcl_conv_stack_bf16 (activations stay on chip) vs five fcl_conv_gemm_bf16 launches: same bf16 roundings,
+    so they agree to fp32 summation order; utterance boundaries inside and across tiles, 1-frame utterance."""
+    eng, sd, hp = bf16_engines("S")
+    lens = [300, 5, 1, 112, 113, 64, 700]
+    F_ = sum(lens)
+    before = torch.randn(F_, 80, generator=torch.Generator().manual_seed(1)).cuda()
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    lo = torch.from_numpy(np.repeat(off[:-1], lens)).cuda()
+    hi = torch.from_numpy(np.repeat(off[1:], lens)).cuda()
+    ufo = torch.from_numpy(off).cuda()
+    tiles = eng.conv_tiles(ufo, len(lens), sum((n + 127) // 128 for n in lens))
+    ref = eng.postnet(before, (lo, hi, tiles), F_)                          # layer by layer
+    fused = eng.postnet(before, (lo, hi, tiles, (ufo, len(lens))), F_)      # fused stack
+    torch.cuda.synchronize()
+    assert torch.isfinite(fused).all()
+    assert err(fused.cpu(), ref.cpu())[0] < 2e-4
+    for k in range(len(lens)):
+        o = restate.postnet(sd, before[off[k]:off[k + 1]].cpu())
+        assert err(fused[off[k]:off[k + 1]].cpu(), o)[0] < 8e-2
