@@ -274,7 +274,7 @@ def main():
         }
         if not args.no_extra:
             line["p50_utt_latency_ms"] = latency_p50(m, args, dev)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only (torchrun pins OMP threads to 1)
             fps, n, fr, dt, thr = cpu_port_time(args.model, xs, ds, budget_s=15.0, seed=args.seed)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": thr, "kind": "port",
                                     "sample": f"first {n} utterances ({fr} frames) of the same workload, per-utterance "
