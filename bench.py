@@ -174,6 +174,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/fcl_nccl_%h_%p.log")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     m = M.from_preset(args.model, seed=args.seed, device=dev, precision=args.precision)
@@ -191,13 +192,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    counts = fdist.exchange_counts(n_frames, dev) if world > 1 else None   # forced durations: known before the pass
+
     def one_step(timed):
         flush.fill_(rank + 1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         eng.stage_events = [] if timed else None
         e0.record()
         res = eng.run_uploaded(pl, dinp, m.hp.zoneout_rate, args.dropout, 1)
-        gathered = fdist.gather_mels(res.out) if world > 1 else None
+        gathered = None
+        if world > 1:
+            with eng.stage("gather"):
+                gathered = fdist.gather_mels(res.out, counts=counts)
         e1.record()
         return e0, e1, res, eng.stage_events, gathered
 

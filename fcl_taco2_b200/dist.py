@@ -21,15 +21,23 @@ def my_shard(costs, rank: int | None = None, world_size: int | None = None):
     return shard_utterances(costs, world_size)[rank]
 
 
-def gather_mels(out: torch.Tensor, dst: int = 0, group=None):
-    """out (F_rank, odim) on every rank -> on `dst`: (list of per-rank tensors); elsewhere None.
-    Message sizes are data dependent, so counts are exchanged first (world_size * 8 bytes)."""
-    ws, rank = dist.get_world_size(group), dist.get_rank(group)
-    odim = out.shape[1]
-    cnt = torch.tensor([out.shape[0]], dtype=torch.int64, device=out.device)
+def exchange_counts(n_frames: int, device, group=None):
+    """Frame count of every rank (world_size * 8 bytes). With forced durations the count is known on the host
+    before any kernel runs, so this tiny collective can be issued at the START of a pass."""
+    ws = dist.get_world_size(group)
+    cnt = torch.tensor([n_frames], dtype=torch.int64, device=device)
     cnts = [torch.empty_like(cnt) for _ in range(ws)]
     dist.all_gather(cnts, cnt, group=group)
-    counts = [int(c.item()) for c in cnts]
+    return [int(c.item()) for c in cnts]
+
+
+def gather_mels(out: torch.Tensor, dst: int = 0, group=None, counts=None):
+    """out (F_rank, odim) on every rank -> on `dst`: (list of per-rank tensors); elsewhere None.
+    Message sizes are data dependent: `counts` (from exchange_counts) avoids a host sync at the end of the pass."""
+    ws, rank = dist.get_world_size(group), dist.get_rank(group)
+    odim = out.shape[1]
+    if counts is None:
+        counts = exchange_counts(out.shape[0], out.device, group)
     if ws == 1:
         return [out]
     if rank == dst:
