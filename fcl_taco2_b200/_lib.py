@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -60,7 +60,7 @@ class ConvStackTilesParams(C.Structure):
 
 class ConvStackParams(C.Structure):
     _fields_ = [("n_layers", i32), ("taps", i32), ("layers", ConvLayer * MAX_STACK_LAYERS), ("in_", ptr), ("ld_in", i32),
-                ("gather", ptr), ("tiles", ptr), ("n_tiles_dev", ptr), ("n_tiles", i32), ("residual", ptr),
+                ("in_channels", i32), ("b_stages", i32), ("gather", ptr), ("tiles", ptr), ("n_tiles_dev", ptr), ("n_tiles", i32), ("residual", ptr),
                 ("ldr", i32), ("out", ptr), ("ldo", i32)]
 
 

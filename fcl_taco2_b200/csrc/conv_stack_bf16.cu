@@ -21,17 +21,17 @@ using namespace umma;
 constexpr int kCsThreads = 192;
 constexpr int kCsWinRows = 136;
 constexpr uint32_t kCsSlab = kCsWinRows * 16;       // 2176 B per 8-channel slab
-constexpr int kCsBStages = 2;
+constexpr int kCsMaxBStages = 8;
 
 struct CsShared {
   uint64_t img_ready[FCL_MAX_STACK_LAYERS];         // image of layer l complete (128 thread arrivals)
-  uint64_t b_full[kCsBStages], b_empty[kCsBStages];
+  uint64_t b_full[kCsMaxBStages], b_empty[kCsMaxBStages];
   uint64_t accum;
   uint32_t tmem_base;
 };
 
 __global__ void __launch_bounds__(kCsThreads)
-conv_stack_bf16_kernel(FclConvStackParams p, uint32_t img_bytes, uint32_t b_slot_bytes, uint32_t tmem_cols) {
+conv_stack_bf16_kernel(FclConvStackParams p, uint32_t img_bytes, uint32_t b_slot_bytes, uint32_t tmem_cols, int kCsBStages) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ CsShared sh;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -40,8 +40,9 @@ conv_stack_bf16_kernel(FclConvStackParams p, uint32_t img_bytes, uint32_t b_slot
   const int L = p.n_layers, taps = p.taps, h = taps >> 1;
   const int row0 = p.tiles[4 * tile], seg_lo = p.tiles[4 * tile + 1], seg_hi = p.tiles[4 * tile + 2];
   const int gbase = row0 - L * h;                    // global row of image row 0
-  uint8_t* img[2] = {smem, smem + img_bytes};
-  uint8_t* b_ring = smem + 2 * (size_t)img_bytes;
+  // ONE image buffer: a layer's epilogue runs after all of its MMAs retired, so it overwrites its own input
+  uint8_t* img[2] = {smem, smem};
+  uint8_t* b_ring = smem + (size_t)img_bytes;
 
   if (tid == 0) {
     for (int l = 0; l < L; ++l) mbar_init(&sh.img_ready[l], 128);
@@ -58,7 +59,8 @@ conv_stack_bf16_kernel(FclConvStackParams p, uint32_t img_bytes, uint32_t b_slot
   if (warp < 4) {
     // ------------------------------------------------ layer-0 image: coalesced fp32 loads -> bf16
     {
-      const int cin = p.layers[0].cin;
+      const int cin = p.layers[0].cin;               // may be zero-padded beyond the real input width
+      const int cin_real = p.in_channels;
       const int kq = lane >> 3;
       for (int rg = warp; rg < kCsWinRows / 8; rg += 4) {
         const int j = rg * 8 + (lane & 7);
@@ -71,7 +73,7 @@ conv_stack_bf16_kernel(FclConvStackParams p, uint32_t img_bytes, uint32_t b_slot
 #pragma unroll
           for (int kg = 0; kg < 4; ++kg) {
             v[kg] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (src && k0 + 16 * kg < cin) v[kg] = __ldg(reinterpret_cast<const float4*>(src + k0 + 16 * kg));
+            if (src && k0 + 16 * kg < cin_real) v[kg] = __ldg(reinterpret_cast<const float4*>(src + k0 + 16 * kg));
           }
 #pragma unroll
           for (int kg = 0; kg < 4; ++kg) {
@@ -269,9 +271,20 @@ extern "C" int fcl_conv_stack_bf16(const FclConvStackParams* p, void* stream) {
     const size_t bb = (size_t)ly.cout * ly.kstage * 2;
     b_slot = bb > b_slot ? bb : b_slot;
   }
+  FCL_REQUIRE(p->in_channels > 0 && p->in_channels <= p->layers[0].cin && p->in_channels % 16 == 0, "bad in_channels");
   FCL_REQUIRE(p->ld_in % 4 == 0 && p->ldo % 4 == 0 && (!p->residual || p->ldr % 4 == 0), "leading dims must be multiples of 4");
   const size_t img_bytes = (size_t)(max_c / 8) * kCsSlab;
-  const size_t smem = 2 * img_bytes + kCsBStages * b_slot;
+  // The weight ring must hold enough bytes in flight to cover the L2 round trip (~2 k cycles x ~60 B/clk per SM):
+  // as many stages as fit beside the two images (one CTA per SM when that is what it takes).
+  if (img_bytes + 2 * b_slot > 216 * 1024) {
+    set_error("fcl_conv_stack_bf16: %zu B shared memory needed (channels too wide to fuse)", img_bytes + 2 * b_slot);
+    return FCL_EUNSUPPORTED;
+  }
+  // measured: the per-tile chain (load, then L x [MMA -> epilogue]) is latency-bound, so co-resident CTAs matter
+  // more than a deep weight ring: 2 stages, as many CTAs per SM as shared memory / TMEM allow.
+  int b_stages = p->b_stages > 0 ? p->b_stages : 2;
+  b_stages = b_stages > kCsMaxBStages ? kCsMaxBStages : b_stages;
+  const size_t smem = img_bytes + (size_t)b_stages * b_slot;
   if (smem > 216 * 1024) { set_error("fcl_conv_stack_bf16: %zu B shared memory needed (channels too wide to fuse)", smem); return FCL_EUNSUPPORTED; }
   static bool attr_done = false;
   if (!attr_done) {
@@ -280,6 +293,6 @@ extern "C" int fcl_conv_stack_bf16(const FclConvStackParams* p, void* stream) {
     attr_done = true;
   }
   conv_stack_bf16_kernel<<<p->n_tiles, kCsThreads, smem, as_stream(stream)>>>(*p, (uint32_t)img_bytes, (uint32_t)b_slot,
-                                                                               tmem_cols_pow2((uint32_t)max_cout));
+                                                                               tmem_cols_pow2((uint32_t)max_cout), b_stages);
   return check_launch("fcl_conv_stack_bf16");
 }

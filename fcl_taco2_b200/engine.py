@@ -67,6 +67,7 @@ class Engine:
             self.dec_c_ws = torch.empty((self.n_slots * c_f,), dtype=torch.float32, device=self.device)
         self.head_b = {s: float(packed[f"{s}_head_b"][0]) for s in ("dur", "pitch", "energy")}
         self.launches = 0
+        self.use_encoder_stack = False   # measured: with 256 channels only a 2-stage weight ring fits beside the images
         self.stage_events = None      # when a list: (stage, start_event, stop_event) appended per stage (bench.py)
 
     # ------------------------------------------------------------------ launch helpers
@@ -123,15 +124,31 @@ class Engine:
         self._call("fcl_layernorm_f32", p)
 
     # ------------------------------------------------------------------ stages
-    def encoder(self, ids, utt_off, seg, n_utts):
+    def encoder(self, ids, utt_off, seg, n_utts, lens=None):
         hp, w = self.hp, self.w
         P, E = ids.shape[0], hp.eunits
+        x = None
+        if self.precision == "bf16" and self.use_encoder_stack and all(f"enc_conv{l}" in self.wb for l in range(3)):
+            if lens is None:
+                lens = np.diff(utt_off.cpu().numpy().astype(np.int64))
+            x = self.conv_stack([f"enc_conv{l}" for l in range(3)], [ACT_RELU] * 3, w["embed"], hp.embed_dim, P, utt_off,
+                                n_utts, lambda s: int(((lens + s - 1) // s).sum()), gather=ids)
+        if x is None:
+            x = self._encoder_convs(ids, seg, P)
+        return self._encoder_lstm(x, utt_off, n_utts, P)
+
+    def _encoder_convs(self, ids, seg, P):
+        hp, w = self.hp, self.w
         x = self.conv_gemm(w["embed"], w["enc_conv0_w"], w["enc_conv0_b"], P, hp.embed_dim, hp.econv_chans, 5,
                            ACT_RELU, seg=seg, gather=ids, key="enc_conv0")
         x = self.conv_gemm(x, w["enc_conv1_w"], w["enc_conv1_b"], P, hp.econv_chans, hp.econv_chans, 5, ACT_RELU, seg=seg,
                            key="enc_conv1")
-        x = self.conv_gemm(x, w["enc_conv2_w"], w["enc_conv2_b"], P, hp.econv_chans, hp.econv_chans, 5, ACT_RELU, seg=seg,
-                           key="enc_conv2")
+        return self.conv_gemm(x, w["enc_conv2_w"], w["enc_conv2_b"], P, hp.econv_chans, hp.econv_chans, 5, ACT_RELU,
+                              seg=seg, key="enc_conv2")
+
+    def _encoder_lstm(self, x, utt_off, n_utts, P):
+        hp, w = self.hp, self.w
+        E = hp.eunits
         h = torch.empty((P, E), dtype=torch.float32, device=self.device)
         if self.precision == "bf16" and getattr(self, "blstm_whh_bf16", None) is not None:
             gx = torch.empty((P, 4 * E), dtype=torch.bfloat16, device=self.device)
@@ -253,7 +270,7 @@ class Engine:
         return before
 
     def conv_stack(self, keys, acts, x, ld_in, rows, seg_off, n_segs, max_len_sum_tiles, taps=5, gather=None,
-                   residual=None):
+                   residual=None, wkeys=None):
         """Fused conv stack (fcl_conv_stack_bf16) over the layers `keys`; returns None when the stack does not
         fit on chip (caller falls back to layer-by-layer fcl_conv_gemm_bf16)."""
         L = len(keys)
@@ -261,14 +278,17 @@ class Engine:
         layers = (_lib.ConvLayer * _lib.MAX_STACK_LAYERS)()
         max_c, b_slot = 0, 0
         for l, key in enumerate(keys):
-            wp, ntile, kstage = self.wb[key]
+            wp, ntile, kstage = self.wb[(wkeys or keys)[l]]
             taps_l, cin, cout = self.w[key + "_w"].shape
             if ntile != cout or taps_l != taps:
                 return None
+            if l == 0:
+                in_channels = cin
+                cin = (cin + kstage - 1) // kstage * kstage        # zero-padded by the packer
             layers[l] = _lib.ConvLayer(cin=cin, cout=cout, kstage=kstage, act=acts[l], w_packed=dptr(wp),
                                        bias=dptr(self.w[key + "_b"]))
             max_c, b_slot = max(max_c, cin), max(b_slot, cout * kstage * 2)
-        if 2 * (max_c // 8) * 2176 + 2 * b_slot > 216 * 1024:
+        if (max_c // 8) * 2176 + 2 * b_slot > 216 * 1024:
             return None
         dev = self.device
         max_tiles = max_len_sum_tiles(stride)
@@ -280,7 +300,7 @@ class Engine:
         cout_last = layers[L - 1].cout
         out = torch.empty((rows, cout_last), dtype=torch.float32, device=dev)
         self._call("fcl_conv_stack_bf16", _lib.ConvStackParams(n_layers=L, taps=taps, layers=layers, in_=dptr(x), ld_in=ld_in,
-                                                               gather=dptr(gather), tiles=dptr(tiles), n_tiles_dev=dptr(count),
+                                                               in_channels=in_channels, b_stages=0, gather=dptr(gather), tiles=dptr(tiles), n_tiles_dev=dptr(count),
                                                                n_tiles=max_tiles, residual=dptr(residual), ldr=cout_last,
                                                                out=dptr(out), ldo=cout_last))
         return out
@@ -291,7 +311,9 @@ class Engine:
         if self.precision == "bf16" and len(fseg) > 3 and all(f"post_conv{l}" in self.wb for l in range(5)):
             utt_frame_off, n_utts = fseg[3]
             out = self.conv_stack([f"post_conv{l}" for l in range(5)], [ACT_TANH] * 4 + [ACT_NONE], before, O, n_frames,
-                                  utt_frame_off, n_utts, lambda s: (n_frames + s - 1) // s + n_utts, residual=before)
+                                  utt_frame_off, n_utts, lambda s: (n_frames + s - 1) // s + n_utts, residual=before,
+                                  wkeys=(["post_stack0"] if "post_stack0" in self.wb else ["post_conv0"]) +
+                                        [f"post_conv{l}" for l in range(1, 5)])
             if out is not None:
                 return out
         x = self.conv_gemm(before, w["post_conv0_w"], w["post_conv0_b"], n_frames, O, C, 5, ACT_TANH, seg=fseg,
@@ -364,7 +386,7 @@ class Engine:
         lens = np.diff(plan.utt_off.astype(np.int64))
         with self.stage("encoder"):
             seg = (d["seg_lo"], d["seg_hi"], self.conv_tiles(d["utt_off"], B, int(((lens + 127) // 128).sum())))
-            h = self.encoder(d["ids"], d["utt_off"], seg, B)
+            h = self.encoder(d["ids"], d["utt_off"], seg, B, lens=lens)
         need_pred_dur = plan.dur is None
         dlog = dur_pred = None
         with self.stage("predictors"):

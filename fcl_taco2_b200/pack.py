@@ -125,6 +125,16 @@ def pack_bf16(packed_fp32: dict) -> dict:
     for key in GEMM_KEYS:
         w = packed_fp32[key if key == "blstm_wih" else key + "_w"]
         out[key] = pack_conv_bf16(w)
+    # first postnet layer for the fused stack: input channels zero-padded to a multiple of 64 so that every
+    # weight stage of the stack is (cout x 64) and the ring slots stay small (three CTAs per SM)
+    w0 = packed_fp32["post_conv0_w"]
+    taps, cin, cout = w0.shape
+    if cin % 64:
+        pad = torch.zeros(taps, (cin + 63) // 64 * 64, cout)
+        pad[:, :cin] = w0
+        w0 = pad
+    if cout <= 256 and cout % 16 == 0:
+        out["post_stack0"] = pack_conv_bf16(w0, cout, 64)
     return out
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 11
+#define FCL_ABI_VERSION 12
 
 enum {
   FCL_OK = 0,
@@ -170,6 +170,8 @@ typedef struct {
   FclConvLayer layers[FCL_MAX_STACK_LAYERS];
   const float* in;                    /* (rows, ld_in) fp32, or the embedding table when gather != NULL       */
   int32_t ld_in;
+  int32_t in_channels;                /* real input width (<= layers[0].cin, which may be zero-padded to 64)  */
+  int32_t b_stages;                   /* weight ring depth (0 = default 2)                                    */
   const int64_t* gather;
   const int32_t* tiles;               /* from fcl_conv_stack_tiles                                            */
   const int32_t* n_tiles_dev;         /* optional device tile count (grid = n_tiles is an upper bound)        */
