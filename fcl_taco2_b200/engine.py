@@ -312,8 +312,8 @@ class Engine:
             utt_frame_off, n_utts = fseg[3]
             out = self.conv_stack([f"post_conv{l}" for l in range(5)], [ACT_TANH] * 4 + [ACT_NONE], before, O, n_frames,
                                   utt_frame_off, n_utts, lambda s: (n_frames + s - 1) // s + n_utts, residual=before,
-                                  wkeys=(["post_stack0"] if "post_stack0" in self.wb else ["post_conv0"]) +
-                                        [f"post_conv{l}" for l in range(1, 5)])
+                                  wkeys=[f"post_stack{l}" if f"post_stack{l}" in self.wb else f"post_conv{l}"
+                                         for l in range(5)])
             if out is not None:
                 return out
         x = self.conv_gemm(before, w["post_conv0_w"], w["post_conv0_b"], n_frames, O, C, 5, ACT_TANH, seg=fseg,

@@ -114,6 +114,8 @@ def pack_conv_bf16(w: torch.Tensor, ntile: int | None = None, kstage: int | None
     return x.to(torch.bfloat16).reshape(-1).contiguous(), ntile, kstage
 
 
+STACK_KSTAGE = 32
+
 GEMM_KEYS = ["enc_conv0", "enc_conv1", "enc_conv2", "blstm_wih", "dur_conv0", "dur_conv1", "pitch_conv0", "pitch_conv1",
              "energy_conv0", "energy_conv1", "post_conv0", "post_conv1", "post_conv2",
              "post_conv3", "post_conv4"]
@@ -125,16 +127,17 @@ def pack_bf16(packed_fp32: dict) -> dict:
     for key in GEMM_KEYS:
         w = packed_fp32[key if key == "blstm_wih" else key + "_w"]
         out[key] = pack_conv_bf16(w)
-    # first postnet layer for the fused stack: input channels zero-padded to a multiple of 64 so that every
-    # weight stage of the stack is (cout x 64) and the ring slots stay small (three CTAs per SM)
-    w0 = packed_fp32["post_conv0_w"]
-    taps, cin, cout = w0.shape
-    if cin % 64:
-        pad = torch.zeros(taps, (cin + 63) // 64 * 64, cout)
-        pad[:, :cin] = w0
-        w0 = pad
-    if cout <= 256 and cout % 16 == 0:
-        out["post_stack0"] = pack_conv_bf16(w0, cout, 64)
+    # postnet layers for the fused stack: K stages of STACK_KSTAGE channels (first layer's input channels zero-padded
+    # to a multiple of it) so the weight-ring slots stay small and several CTAs share an SM
+    for l in range(5):
+        w = packed_fp32[f"post_conv{l}_w"]
+        taps, cin, cout = w.shape
+        if cin % STACK_KSTAGE:
+            pad = torch.zeros(taps, (cin + STACK_KSTAGE - 1) // STACK_KSTAGE * STACK_KSTAGE, cout)
+            pad[:, :cin] = w
+            w = pad
+        if cout <= 256 and cout % 16 == 0:
+            out[f"post_stack{l}"] = pack_conv_bf16(w, cout, STACK_KSTAGE)
     return out
 
 
