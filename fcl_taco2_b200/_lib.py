@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -91,7 +91,8 @@ class DecoderBf16Params(C.Structure):
     _fields_ = [("n_rows", i32), ("n_tiles", i32), ("n_slots", i32), ("eunits", i32), ("dunits", i32),
                 ("prenet_units", i32), ("odim", i32), ("order", ptr), ("dur", ptr), ("frame_off", ptr),
                 ("row_utt", ptr), ("row_phone", ptr), ("hn_img", ptr), ("w_stream", ptr), ("bp0", ptr), ("bp1", ptr),
-                ("wpos", ptr), ("b0", ptr), ("b1", ptr), ("act_ws", ptr), ("c_ws", ptr), ("before", ptr),
+                ("wpos", ptr), ("b0", ptr), ("b1", ptr), ("group", i32), ("act_priv", ptr), ("act_shared", ptr),
+                ("c_ws", ptr), ("group_sync", ptr), ("before", ptr),
                 ("zoneout", f32), ("dropout_p", f32), ("dropout_seed", u64), ("tile_slot", ptr), ("tile_rank", ptr),
                 ("trace", ptr), ("trace_cap", i32)]
 
@@ -170,7 +171,8 @@ def load():
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(st), C.c_void_p]
     lib.fcl_decoder_bf16_workspace.restype = C.c_int
-    lib.fcl_decoder_bf16_workspace.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.fcl_decoder_bf16_workspace.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                               C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 
@@ -189,9 +191,9 @@ def dptr(t):
 
 
 def decoder_bf16_workspace(prenet_units: int, dunits: int):
-    """-> (activation-scratch bytes per CTA slot, cell-state floats per CTA slot)."""
-    a, c = C.c_int64(), C.c_int64()
-    rc = load().fcl_decoder_bf16_workspace(prenet_units, dunits, C.byref(a), C.byref(c))
+    """-> (private scratch bytes per CTA, shared scratch bytes per group, cell-state floats per CTA)."""
+    a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+    rc = load().fcl_decoder_bf16_workspace(prenet_units, dunits, C.byref(a), C.byref(b), C.byref(c))
     if rc != 0:
         raise FclError("fcl_decoder_bf16_workspace failed")
-    return a.value, c.value
+    return a.value, b.value, c.value

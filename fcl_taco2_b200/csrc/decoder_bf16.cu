@@ -48,13 +48,15 @@ struct DbShared {
   int my_tiles[kDbMaxTilesPerCta];
 };
 
-// activation scratch of one CTA slot (bytes): x1 | x2 | z0a z0b z1a z1b
+// activation scratch (bytes). Private to a CTA: x1 | x2. Shared by the CTAs of a group (which split the gate
+// columns of one tile): two sets (even / odd tile of the group) of z0a z0b z1a z1b.
+__host__ __device__ inline size_t db_priv_bytes(int U) { return 2 * (size_t)U * 128 * 2; }
 __host__ __device__ inline size_t db_x1_off() { return 0; }
 __host__ __device__ inline size_t db_x2_off(int U) { return (size_t)U * 128 * 2; }
-__host__ __device__ inline size_t db_z_off(int U, int H, int which /*0..3: z0a z0b z1a z1b*/) {
-  return 2 * (size_t)U * 128 * 2 + (size_t)which * H * 128 * 2;
+__host__ __device__ inline size_t db_shared_bytes(int H) { return 8 * (size_t)H * 128 * 2; }
+__host__ __device__ inline size_t db_z_off(int H, int set, int which /*0..3: z0a z0b z1a z1b*/) {
+  return (size_t)(set * 4 + which) * H * 128 * 2;
 }
-__host__ __device__ inline size_t db_act_bytes(int U, int H) { return db_z_off(U, H, 4); }
 
 // tile visited at round `tk` by this CTA: from the LPT schedule (fcl_decoder_schedule) staged in shared memory.
 #define DB_TILE(tk) ((tk) < sh.n_my_tiles ? sh.my_tiles[tk] : -1)
@@ -75,6 +77,23 @@ __device__ __forceinline__ void db_trace(const FclDecoderBf16Params& p, int id) 
 
 struct DbDims {
   int kU, kH, kE, gate_chunks;
+  int C, cr;                       // CTAs cooperating on a tile, rank of this CTA among them
+  // which chunks of a phase this CTA computes: the gate chunks are dealt round-robin over the group, the small
+  // prenet phases are computed redundantly by everyone (their outputs stay private), feat_out by rank 0 only
+  __device__ __forceinline__ bool owns(int phase, int c) const {
+    if (phase == 1 || phase == 2) return (c % C) == cr;
+    if (phase == 3 && c == 0) return cr == 0;
+    return true;
+  }
+  // byte offset of chunk c of a phase in the weight stream (blocks are [chunk][k stage])
+  __device__ __forceinline__ size_t w_off(int phase, int c, uint32_t bw, uint32_t bf) const {
+    const size_t l0 = (size_t)kU * bw, l1 = l0 + (size_t)gate_chunks * (kE + kH + kU) * bw;
+    const size_t f = l1 + (size_t)gate_chunks * 2 * kH * bw, pc = f + (size_t)(kE + kH) * bf;
+    if (phase == 0) return 0;
+    if (phase == 1) return l0 + (size_t)c * (kE + kH + kU) * bw;
+    if (phase == 2) return l1 + (size_t)c * 2 * kH * bw;
+    return c == 0 ? f : pc;
+  }
   __device__ __forceinline__ int nchunks(int phase, bool last_step) const {
     return phase == 0 ? 1 : phase == 3 ? (last_step ? 1 : 2) : gate_chunks;
   }
@@ -122,14 +141,17 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
   const int H = p.dunits, U = p.prenet_units, O = p.odim, E = p.eunits;
   DbDims dm;
   dm.kU = U / 64; dm.kH = H / 64; dm.kE = E / 64; dm.gate_chunks = 4 * H / 256;
-  uint8_t* act = reinterpret_cast<uint8_t*>(p.act_ws) + (size_t)blockIdx.x * db_act_bytes(U, H);
+  dm.C = p.group; dm.cr = (int)blockIdx.x % p.group;
+  const int grp = (int)blockIdx.x / p.group;
+  uint8_t* act = reinterpret_cast<uint8_t*>(p.act_priv) + (size_t)blockIdx.x * db_priv_bytes(U);          // x1 | x2
+  uint8_t* zsh = reinterpret_cast<uint8_t*>(p.act_shared) + (size_t)grp * db_shared_bytes(H);             // z images
   float* cws = p.c_ws + (size_t)blockIdx.x * 2 * H * 128;
 
   // this CTA's tile list (longest-processing-time schedule)
   if (tid == 0) sh.n_my_tiles = 0;
   __syncthreads();
   for (int t = tid; t < p.n_tiles; t += kDbThreads) {
-    if (p.tile_slot[t] == (int)blockIdx.x) {
+    if (p.tile_slot[t] == grp) {
       const int k = p.tile_rank[t];
       if (k < kDbMaxTilesPerCta) { sh.my_tiles[k] = t; atomicMax(&sh.n_my_tiles, k + 1); }
     }
@@ -152,23 +174,44 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
     if (elect_one()) {
       uint32_t stage = 0, sphase = 0;                 // ring position / parity
       uint32_t rdy[4] = {0, 0, 0, 0};                 // parity of each a_ready barrier
+      int sync_ev[2] = {0, 0};                        // group barriers passed so far (z0', z1')
       for (int tk = 0, tile; (tile = DB_TILE(tk)) >= 0; ++tk) {
         const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
         const uint8_t* himg = reinterpret_cast<const uint8_t*>(p.hn_img) + (size_t)tile * E * 128 * 2;
+        const int zset = tk & 1;
         for (int m = 0; m < steps; ++m) {
           const int zp = m & 1;
-          const uint8_t* z0cur = act + db_z_off(U, H, zp), *z0new = act + db_z_off(U, H, zp ^ 1);
-          const uint8_t* z1cur = act + db_z_off(U, H, 2 + zp), *z1new = act + db_z_off(U, H, 2 + (zp ^ 1));
-          const uint8_t* wptr = reinterpret_cast<const uint8_t*>(p.w_stream);
+          const uint8_t* z0cur = zsh + db_z_off(H, zset, zp), *z0new = zsh + db_z_off(H, zset, zp ^ 1);
+          const uint8_t* z1cur = zsh + db_z_off(H, zset, 2 + zp), *z1new = zsh + db_z_off(H, zset, 2 + (zp ^ 1));
           for (int phase = 0; phase < 4; ++phase) {
             if (tid == 0) db_trace(p, 600 + phase);
             const int nch = dm.nchunks(phase, m + 1 == steps), kst = dm.kstages(phase), late = dm.late_stage(phase);
+            bool waited = false;
+            if (dm.C > 1 && phase >= 2) {
+              // group mode: tell the other CTAs of the tile that this CTA's slice of z0' (z1') is written
+              mbar_wait(&sh.a_ready[phase], rdy[phase]);
+              rdy[phase] ^= 1u;
+              __threadfence();
+              atomicAdd(p.group_sync + 2 * grp + (phase - 2), 1);
+              ++sync_ev[phase - 2];
+            }
             for (int c = 0; c < nch; ++c) {
+              if (!dm.owns(phase, c)) continue;
               const uint32_t bb = (phase == 3 && c == 0) ? b_bytes_feat : b_bytes_wide;
+              const uint8_t* wptr = reinterpret_cast<const uint8_t*>(p.w_stream) + dm.w_off(phase, c, b_bytes_wide, b_bytes_feat);
               for (int ks = 0; ks < kst; ++ks) {
-                if (c == 0 && ks == late) {            // operand written by the previous phase's epilogue
-                  mbar_wait(&sh.a_ready[phase], rdy[phase]);
-                  rdy[phase] ^= 1u;
+                if (!waited && ks == late) {           // operand written by the previous phase's epilogue(s)
+                  waited = true;
+                  if (dm.C > 1 && phase >= 2) {
+                    const int target = sync_ev[phase - 2] * dm.C;
+                    const volatile int* ctr = p.group_sync + 2 * grp + (phase - 2);
+                    while (*ctr < target) __nanosleep(64);
+                    __threadfence();
+                    fence_proxy_async_all();
+                  } else {
+                    mbar_wait(&sh.a_ready[phase], rdy[phase]);
+                    rdy[phase] ^= 1u;
+                  }
                 }
                 const uint8_t* asrc;
                 if (phase == 0) asrc = act + db_x1_off() + (size_t)ks * kABytes;
@@ -185,6 +228,10 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
                 wptr += bb;
                 if (++stage == kDbStages) { stage = 0; sphase ^= 1u; }
               }
+            }
+            if (!waited && !(dm.C > 1 && phase >= 2)) {   // no owned chunk in this phase: keep the barrier parity in step
+              mbar_wait(&sh.a_ready[phase], rdy[phase]);
+              rdy[phase] ^= 1u;
             }
           }
         }
@@ -203,6 +250,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
           for (int phase = 0; phase < 4; ++phase) {
             const int nch = dm.nchunks(phase, m + 1 == steps), kst = dm.kstages(phase);
             for (int c = 0; c < nch; ++c) {
+              if (!dm.owns(phase, c)) continue;
               const bool feat = phase == 3 && c == 0;
               const uint32_t ncols = feat ? (uint32_t)O : 256u;
               const uint32_t idesc = feat ? idesc_feat : idesc_wide;
@@ -259,6 +307,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
       }
       const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
       if (steps == 0) continue;
+      const int zset = tk & 1;
       // ---- tile init: x1 of step 0 (the first input frame is zero: prenet.0 sees only its bias) and zero z images
       {
 #pragma unroll 1
@@ -266,9 +315,11 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
           prenet_store16(nullptr, p.bp0, cs * 64 + g * 16, r, act + db_x1_off(), use_drop, drop_thr, drop_scale,
                          p.dropout_seed, (uint32_t)utt, (uint32_t)ph, 0u, 0u);
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        // (in group mode every CTA of the group zeroes the same images with the same zeros; the set alternates per
+        // tile so a CTA that is one tile ahead never touches images a slower CTA still reads)
         for (int kc = cs; kc < H / 8; kc += 4) {
-          *reinterpret_cast<uint4*>(act + db_z_off(U, H, 0) + ((size_t)kc * 128 + r) * 16) = z4;
-          *reinterpret_cast<uint4*>(act + db_z_off(U, H, 2) + ((size_t)kc * 128 + r) * 16) = z4;
+          *reinterpret_cast<uint4*>(zsh + db_z_off(H, zset, 0) + ((size_t)kc * 128 + r) * 16) = z4;
+          *reinterpret_cast<uint4*>(zsh + db_z_off(H, zset, 2) + ((size_t)kc * 128 + r) * 16) = z4;
         }
         fence_proxy_async_all();
         mbar_arrive(&sh.a_ready[0]);
@@ -276,8 +327,8 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
 
       for (int m = 0; m < steps; ++m) {
         const int zp = m & 1;
-        uint8_t* z0cur = act + db_z_off(U, H, zp), *z0new = act + db_z_off(U, H, zp ^ 1);
-        uint8_t* z1cur = act + db_z_off(U, H, 2 + zp), *z1new = act + db_z_off(U, H, 2 + (zp ^ 1));
+        uint8_t* z0cur = zsh + db_z_off(H, zset, zp), *z0new = zsh + db_z_off(H, zset, zp ^ 1);
+        uint8_t* z1cur = zsh + db_z_off(H, zset, 2 + zp), *z1new = zsh + db_z_off(H, zset, 2 + (zp ^ 1));
         const float pos = (row >= 0 && m < d) ? __fdiv_rn((float)m, (float)d) : 0.f;
 
         // ---------------- P1: prenet layer 1 (bias, ReLU, dropout) -> x2 image; 64 columns per thread
@@ -313,18 +364,19 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
           const float* bias = layer == 0 ? p.b0 : p.b1;
           float c_cur[16], c_nxt[16];
           uint4 z_cur[2], z_nxt[2];
-          {
-            const int u0 = cs * 16;
+          const int c_first = dm.cr % dm.C;                           // this CTA's chunks: c_first, c_first + C, ...
+          if (c_first < dm.gate_chunks) {
+            const int u0 = c_first * 64 + cs * 16;
 #pragma unroll
             for (int j = 0; j < 16; ++j) c_cur[j] = m == 0 ? 0.f : __ldcg(cl + (size_t)(u0 + j) * 128 + r);
             z_cur[0] = __ldcg(reinterpret_cast<const uint4*>(zcur + ((size_t)(u0 >> 3) * 128 + r) * 16));
             z_cur[1] = __ldcg(reinterpret_cast<const uint4*>(zcur + ((size_t)((u0 >> 3) + 1) * 128 + r) * 16));
           }
 #pragma unroll 1
-          for (int c = 0; c < dm.gate_chunks; ++c) {
+          for (int c = c_first; c < dm.gate_chunks; c += dm.C) {
             const int u0 = c * 64 + cs * 16;                          // first of this thread's 16 hidden units
-            if (c + 1 < dm.gate_chunks) {
-              const int un = u0 + 64;
+            if (c + dm.C < dm.gate_chunks) {
+              const int un = u0 + 64 * dm.C;
 #pragma unroll
               for (int j = 0; j < 16; ++j) c_nxt[j] = m == 0 ? 0.f : __ldcg(cl + (size_t)(un + j) * 128 + r);
               z_nxt[0] = __ldcg(reinterpret_cast<const uint4*>(zcur + ((size_t)(un >> 3) * 128 + r) * 16));
@@ -378,7 +430,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
         }
 
         // ---------------- FP chunk 0: feat_out -> output frame, stored straight to its final (ragged) position
-        {
+        if (dm.owns(3, 0)) {
           const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
           mbar_wait(&sh.tmem_full[buf], use & 1u);
           tc_fence_after();
@@ -472,21 +524,23 @@ extern "C" int fcl_decoder_schedule(const FclDecoderScheduleParams* p, void* str
   return check_launch("fcl_decoder_schedule");
 }
 
-extern "C" int fcl_decoder_bf16_workspace(int32_t prenet_units, int32_t dunits, int64_t* act_bytes_per_slot,
-                                          int64_t* c_floats_per_slot) {
-  if (!act_bytes_per_slot || !c_floats_per_slot) return FCL_EINVAL;
-  *act_bytes_per_slot = (int64_t)fcl::db_act_bytes(prenet_units, dunits);
-  *c_floats_per_slot = (int64_t)2 * dunits * 128;
+extern "C" int fcl_decoder_bf16_workspace(int32_t prenet_units, int32_t dunits, int64_t* priv_bytes_per_cta,
+                                          int64_t* shared_bytes_per_group, int64_t* c_floats_per_cta) {
+  if (!priv_bytes_per_cta || !shared_bytes_per_group || !c_floats_per_cta) return FCL_EINVAL;
+  *priv_bytes_per_cta = (int64_t)fcl::db_priv_bytes(prenet_units);
+  *shared_bytes_per_group = (int64_t)fcl::db_shared_bytes(dunits);
+  *c_floats_per_cta = (int64_t)2 * dunits * 128;
   return FCL_OK;
 }
 
 extern "C" int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream) {
   using namespace fcl;
   FCL_REQUIRE(p && p->order && p->dur && p->frame_off && p->row_utt && p->row_phone && p->hn_img &&
-                  p->w_stream && p->bp0 && p->bp1 && p->wpos && p->b0 && p->b1 && p->act_ws && p->c_ws && p->before &&
-                  p->tile_slot && p->tile_rank,
+                  p->w_stream && p->bp0 && p->bp1 && p->wpos && p->b0 && p->b1 && p->act_priv && p->act_shared &&
+                  p->c_ws && p->before && p->tile_slot && p->tile_rank && p->group_sync,
               "null pointer");
-  FCL_REQUIRE((long long)p->n_tiles <= (long long)kDbMaxTilesPerCta * p->n_slots, "too many tiles for the per-CTA tile list");
+  FCL_REQUIRE(p->group >= 1 && p->group <= 16 && p->n_slots % p->group == 0, "group must divide n_slots (1..16)");
+  FCL_REQUIRE((long long)p->n_tiles <= (long long)kDbMaxTilesPerCta * (p->n_slots / p->group), "too many tiles for the per-CTA tile list");
   FCL_REQUIRE(p->eunits % 64 == 0 && p->eunits >= 64, "eunits must be a multiple of 64");
   FCL_REQUIRE(p->n_rows > 0 && p->n_tiles == (p->n_rows + 127) / 128, "n_tiles must be ceil(n_rows / 128)");
   FCL_REQUIRE(p->prenet_units == 256, "prenet_units must be 256 (one 256-column chunk)");
@@ -501,7 +555,10 @@ extern "C" int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream) {
     if (e != cudaSuccess) { set_error("fcl_decoder_bf16: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
     attr_done = true;
   }
-  const int grid = p->n_tiles < p->n_slots ? p->n_tiles : p->n_slots;
-  decoder_bf16_kernel<<<grid, kDbThreads, smem, as_stream(stream)>>>(*p);
+  // n_slots CTAs = n_slots / group groups; the spin barriers of group mode need every CTA resident: one CTA per SM,
+  // n_slots <= SM count (checked by the caller against fcl_sm_count()).
+  cudaError_t e = cudaMemsetAsync(p->group_sync, 0, sizeof(int32_t) * 2 * (size_t)(p->n_slots / p->group), as_stream(stream));
+  if (e != cudaSuccess) { set_error("fcl_decoder_bf16: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
+  decoder_bf16_kernel<<<p->n_slots, kDbThreads, smem, as_stream(stream)>>>(*p);
   return check_launch("fcl_decoder_bf16");
 }

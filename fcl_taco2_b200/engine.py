@@ -62,11 +62,14 @@ class Engine:
             if "blstm_wih" in self.wb and (4 * (hp.eunits // 2)) % 256 == 0:
                 self.blstm_whh_bf16 = _pack.pack_bilstm_whh_bf16(packed).to(self.device)
             self.n_slots = _lib.load().fcl_sm_count()
-            act_b, c_f = _lib.decoder_bf16_workspace(hp.prenet_units, hp.dunits)
-            self.dec_act_ws = torch.empty((self.n_slots * act_b,), dtype=torch.uint8, device=self.device)
+            priv_b, shared_b, c_f = _lib.decoder_bf16_workspace(hp.prenet_units, hp.dunits)
+            self.dec_act_priv = torch.empty((self.n_slots * priv_b,), dtype=torch.uint8, device=self.device)
+            self.dec_act_shared = torch.empty((self.n_slots * shared_b,), dtype=torch.uint8, device=self.device)
             self.dec_c_ws = torch.empty((self.n_slots * c_f,), dtype=torch.float32, device=self.device)
+            self.dec_group_sync = torch.zeros((2 * self.n_slots,), dtype=torch.int32, device=self.device)
         self.head_b = {s: float(packed[f"{s}_head_b"][0]) for s in ("dur", "pitch", "energy")}
         self.launches = 0
+        self.force_group = 0             # decoder group size override (tests); 0 = choose from the tile count
         self.use_encoder_stack = False   # measured: with 256 channels only a 2-stage weight ring fits beside the images
         self.stage_events = None      # when a list: (stage, start_event, stop_event) appended per stage (bench.py)
 
@@ -248,9 +251,17 @@ class Engine:
             hn_img = torch.empty((n_tiles * 128 * E,), dtype=torch.bfloat16, device=self.device)
             self._call("fcl_pack_rows_bf16", _lib.PackRowsParams(n_rows=P, cols=E, src=dptr(hn), ld=E, order=dptr(order),
                                                                  dst=dptr(hn_img)))
-            n_slots = min(self.n_slots, n_tiles)
+            # few tiles (small batch / one utterance): groups of CTAs split each tile's gate columns so that every SM
+            # streams only its share of the LSTM weights
+            gate_chunks = 4 * H // 256
+            group = 1
+            while group * 2 <= min(gate_chunks, 16) and n_tiles * group * 2 <= self.n_slots:
+                group *= 2
+            group = self.force_group or group
+            n_groups = min(self.n_slots // group, n_tiles)
+            n_slots = n_groups * group
             sched = torch.empty((2, n_tiles), dtype=torch.int32, device=self.device)
-            self._call("fcl_decoder_schedule", _lib.DecoderScheduleParams(n_rows=P, n_tiles=n_tiles, n_slots=n_slots,
+            self._call("fcl_decoder_schedule", _lib.DecoderScheduleParams(n_rows=P, n_tiles=n_tiles, n_slots=n_groups,
                                                                           order=dptr(order), dur=dptr(dur),
                                                                           tile_slot=dptr(sched[0]), tile_rank=dptr(sched[1])))
         before = torch.empty((max(n_frames, 1), O), dtype=torch.float32, device=self.device)
@@ -260,8 +271,10 @@ class Engine:
                                    frame_off=dptr(frame_off), row_utt=dptr(row_utt), row_phone=dptr(row_phone),
                                    hn_img=dptr(hn_img), w_stream=dptr(self.dec_stream),
                                    bp0=dptr(w["dec_bp0"]), bp1=dptr(w["dec_bp1"]), wpos=dptr(w["dec_wpos"]),
-                                   b0=dptr(w["dec_g0h_b"]), b1=dptr(w["dec_b1"]), act_ws=dptr(self.dec_act_ws),
-                                   c_ws=dptr(self.dec_c_ws), before=dptr(before), zoneout=zoneout,
+                                   b0=dptr(w["dec_g0h_b"]), b1=dptr(w["dec_b1"]), group=group,
+                                   act_priv=dptr(self.dec_act_priv), act_shared=dptr(self.dec_act_shared),
+                                   c_ws=dptr(self.dec_c_ws), group_sync=dptr(self.dec_group_sync), before=dptr(before),
+                                   zoneout=zoneout,
                                    dropout_p=dropout_p, dropout_seed=dropout_seed, tile_slot=dptr(sched[0]),
                                    tile_rank=dptr(sched[1]), trace=dptr(trace),
                                    trace_cap=(trace.numel() - 2) // 2 if trace is not None else 0)

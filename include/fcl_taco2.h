@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 12
+#define FCL_ABI_VERSION 13
 
 enum {
   FCL_OK = 0,
@@ -311,7 +311,9 @@ int fcl_pack_rows_bf16(const FclPackRowsParams* p, void* stream);
  *   w_stream      : bf16 weights pre-tiled as UMMA core matrices in consumption order
  *                   prenet.0 (K padded 80->128) | prenet.1 | cell 0 [W_ih0 prenet part ; W_ih0 h part ; W_hh0] |
  *                   cell 1 [W_ih1 ; W_hh1] | feat_out [z part ; h part]  (fcl_taco2_b200/pack.py: pack_decoder_stream)
- *   act_ws / c_ws : per-slot scratch, sizes from fcl_decoder_bf16_workspace()
+ *   act_priv / act_shared / c_ws : scratch, sizes from fcl_decoder_bf16_workspace()
+ *   n_slots       : CTAs launched (<= SM count: the kernel is persistent, one CTA per SM); tiles are assigned to
+ *                   the n_slots / group groups by fcl_decoder_schedule
  */
 typedef struct {
   int32_t n_rows, n_tiles, n_slots, eunits, dunits, prenet_units, odim;
@@ -327,8 +329,13 @@ typedef struct {
   const float* wpos;         /* (4H) gate-interleaved position column of W_ih0             */
   const float* b0;           /* (4H) gate-interleaved b_ih0 + b_hh0                        */
   const float* b1;           /* (4H) gate-interleaved b_ih1 + b_hh1                        */
-  void* act_ws;              /* n_slots * act_bytes_per_slot                               */
-  float* c_ws;               /* n_slots * c_floats_per_slot                                */
+  int32_t group;             /* CTAs that split the gate columns of ONE tile (1 = a tile per CTA). With few tiles
+                                (small batch, single utterance) a group of g CTAs streams 1/g of the LSTM weights each
+                                and exchanges z through L2 with two counter barriers per step.               */
+  void* act_priv;            /* n_slots * priv_bytes_per_cta                               */
+  void* act_shared;          /* (n_slots / group) * shared_bytes_per_group                 */
+  float* c_ws;               /* n_slots * c_floats_per_cta                                 */
+  int32_t* group_sync;       /* (n_slots / group) * 2 counters (zeroed by the launcher)    */
   float* before;             /* out (F, odim)                                              */
   float zoneout;
   float dropout_p;
@@ -348,8 +355,8 @@ typedef struct {
   int32_t* tile_rank;        /* out (n_tiles) */
 } FclDecoderScheduleParams;
 int fcl_decoder_schedule(const FclDecoderScheduleParams* p, void* stream);
-int fcl_decoder_bf16_workspace(int32_t prenet_units, int32_t dunits, int64_t* act_bytes_per_slot,
-                               int64_t* c_floats_per_slot);
+int fcl_decoder_bf16_workspace(int32_t prenet_units, int32_t dunits, int64_t* priv_bytes_per_cta,
+                               int64_t* shared_bytes_per_group, int64_t* c_floats_per_cta);
 int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream);
 
 #ifdef __cplusplus

@@ -193,3 +193,24 @@ def test_fused_postnet_stack_matches_layer_by_layer(bf16_engines):
     for k in range(len(lens)):
         o = restate.postnet(sd, before[off[k]:off[k + 1]].cpu())
         assert err(fused[off[k]:off[k + 1]].cpu(), o)[0] < 8e-2
+
+
+@pytest.mark.parametrize("kind,groups", [("S", [2, 4]), ("T", [4, 16])])
+def test_decoder_group_mode_bit_identical(bf16_engines, kind, groups):
+    """Group mode (several CTAs split one tile's gate columns, z exchanged through L2 with counter barriers) must
+    give exactly the single-CTA-per-tile result: the arithmetic of a row does not depend on which CTA runs a chunk."""
+    eng, sd, hp = bf16_engines(kind)
+    xs, ds = synth.synth_batch(4, 3, fixed_len=40)               # 160 rows: 2 tiles
+    pl = planmod.make_plan(xs, ds)
+    d, _ = eng.upload(pl)
+    hn = torch.randn(pl.n_rows, hp.eunits, generator=torch.Generator().manual_seed(7)).cuda()
+    frame_off, ufo, order, totals = eng.len_reg_scan(d["dur"], d["utt_off"], pl.n_utts)
+    F_ = int(pl.dur.sum())
+    outs = []
+    for g in [1] + groups:
+        eng.force_group = g
+        outs.append(eng.decoder(hn, d["dur"], frame_off, order, d["row_utt"], d["row_phone"], F_, 0.1, 0.5, 5).clone())
+    eng.force_group = 0
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
