@@ -255,8 +255,9 @@ class Engine:
             # streams only its share of the LSTM weights
             gate_chunks = 4 * H // 256
             group = 1
-            while group * 2 <= min(gate_chunks, 16) and n_tiles * group * 2 <= self.n_slots:
-                group *= 2
+            for g in range(2, min(gate_chunks, 16, self.n_slots // max(n_tiles, 1)) + 1):
+                if -(-gate_chunks // g) < -(-gate_chunks // group):      # fewer chunks per CTA
+                    group = g
             group = self.force_group or group
             n_groups = min(self.n_slots // group, n_tiles)
             n_slots = n_groups * group
