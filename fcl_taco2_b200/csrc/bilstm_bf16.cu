@@ -128,6 +128,71 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
     fence_proxy_async_smem();
     mbar_arrive(&sh.h_ready);
 
+    if (R == 32) {
+      // ---- replicated mode: the 32 utterances of the tile occupy all four 32-row quarters of the M = 128 operand
+      // (the same h rows four times), so all 16 epilogue warps share the cell updates: thread (quarter q, column
+      // set cs, lane) owns utterance `lane` and the 4 hidden units (cs*4 + q)*4.. of every chunk; its cell state
+      // stays in registers. The serial chain per step is 4x shorter than with one quarter doing all the work.
+      const int uu = u_first + lane;
+      int off2 = 0, len2 = 0;
+      if (uu < p.n_utts) { off2 = p.utt_off[uu]; len2 = p.utt_off[uu + 1] - off2; }
+      const int usub = (cs * 4 + q) * 4;                     // first unit within a 64-unit chunk
+      float creg[4][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) creg[c][j] = 0.f;
+      for (int t = 0; t < steps; ++t) {
+        const bool active = t < len2;
+        const int grow = off2 + (dir == 0 ? t : len2 - 1 - t);
+        uint8_t* hnew = himg + (size_t)((t + 1) & 1) * himg_bytes;
+        const __nv_bfloat16* gxr = reinterpret_cast<const __nv_bfloat16*>(p.gx) + (size_t)grow * gx_ld + (size_t)dir * 4 * H;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < nch) {
+            const int ub = c * 64 + usub;
+            uint4 g0 = make_uint4(0u, 0u, 0u, 0u), g1 = g0;
+            if (active) {
+              g0 = __ldg(reinterpret_cast<const uint4*>(gxr + 4 * ub));
+              g1 = __ldg(reinterpret_cast<const uint4*>(gxr + 4 * ub) + 1);
+              if (t + 1 < len2 && (usub & 15) == 0) {      // one lane group per 128-byte line pulls the next step's gx into L2
+                const __nv_bfloat16* nx = reinterpret_cast<const __nv_bfloat16*>(p.gx) +
+                                          (size_t)(grow + (dir == 0 ? 1 : -1)) * gx_ld + (size_t)dir * 4 * H + 4 * ub;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+              }
+            }
+            const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
+            mbar_wait(&sh.tmem_full[buf], use & 1u);
+            tc_fence_after();
+            float v[16], hf[4];
+            tmem_ld16(lane_addr + buf * 256u + (uint32_t)(usub * 4), v);
+            const uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w0 = gw[2 * j], w1 = gw[2 * j + 1];
+              const float gi = __uint_as_float(w0 << 16), gf = __uint_as_float(w0 & 0xFFFF0000u);
+              const float gg = __uint_as_float(w1 << 16), go = __uint_as_float(w1 & 0xFFFF0000u);
+              const float ig = sigmoid_fast(v[4 * j] + gi), fg = sigmoid_fast(v[4 * j + 1] + gf);
+              const float cg = tanh_fast(v[4 * j + 2] + gg), og = sigmoid_fast(v[4 * j + 3] + go);
+              const float cn = fmaf(fg, creg[c][j], ig * cg);
+              hf[j] = active ? og * tanh_fast(cn) : 0.f;
+              if (active) creg[c][j] = cn;
+            }
+            tc_fence_before();
+            mbar_arrive(&sh.tmem_empty[buf]);
+            ++chunk_ctr;
+            const uint2 hw = make_uint2(pack_bf16(hf[0], hf[1]), pack_bf16(hf[2], hf[3]));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)                      // all four replicas of this utterance's row
+              *reinterpret_cast<uint2*>(hnew + ((size_t)(ub >> 3) * 128 + k * 32 + lane) * 16 + (ub & 4) * 2) = hw;
+            if (active)
+              *reinterpret_cast<float4*>(p.out + (size_t)grow * 2 * H + (size_t)dir * H + ub) = make_float4(hf[0], hf[1], hf[2], hf[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&sh.h_ready);
+      }
+    } else
     for (int t = 0; t < steps; ++t) {
       const bool active = t < len;
       const int grow = off + (dir == 0 ? t : len - 1 - t);

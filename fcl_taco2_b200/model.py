@@ -196,13 +196,12 @@ class Tacotron2_sa(_TTSBase, torch.nn.Module):
         -> list of (L_i, odim) float32 tensors on the model device, in the order given."""
         to_np = lambda v: v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
         xs = [to_np(x) for x in xs]
-        for x in xs:
-            if x.ndim != 1:
-                raise ValueError("each utterance must be a 1-D id sequence (encoder_sa.py:157)")
-            if x.size and (x.min() < 0 or x.max() >= self.idim):
-                raise ValueError("phoneme id out of range")
+        if any(x.ndim != 1 for x in xs):
+            raise ValueError("each utterance must be a 1-D id sequence (encoder_sa.py:157)")
         conv = lambda vs: None if vs is None else [to_np(v) for v in vs]
         pl = planmod.make_plan(xs, conv(durs), conv(f0s), conv(energies), utt_ids)
+        if pl.ids.min() < 0 or pl.ids.max() >= self.idim:
+            raise ValueError("phoneme id out of range")
         res = self.engine().run(pl, self.hp.zoneout_rate, self._dropout_rate, self._seed_for_call())
         return res if return_result else res.per_utterance()
 

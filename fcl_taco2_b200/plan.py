@@ -28,41 +28,53 @@ class BatchPlan:
 
 
 def make_plan(xs, durs=None, f0s=None, energies=None, utt_ids=None) -> BatchPlan:
+    """Vectorised: one concatenate per input stream + one gather into processing order (no per-utterance numpy
+    calls beyond the concatenation itself) -- this runs inside the end-to-end timed region."""
     B = len(xs)
     if B == 0:
         raise ValueError("empty batch")
-    lens = np.array([len(x) for x in xs], dtype=np.int64)
+    lens = np.fromiter((len(x) for x in xs), dtype=np.int64, count=B)
     if (lens <= 0).any():
         raise ValueError("zero-length utterance")
     perm = np.argsort(-lens, kind="stable")
     utt_ids = np.arange(B, dtype=np.int64) if utt_ids is None else np.asarray(utt_ids, dtype=np.int64)
+    lens_p = lens[perm]
     off = np.zeros(B + 1, dtype=np.int64)
-    off[1:] = np.cumsum(lens[perm])
+    off[1:] = np.cumsum(lens_p)
     P = int(off[-1])
-    ids = np.concatenate([np.asarray(xs[i], dtype=np.int64).reshape(-1) for i in perm])
-    rep = np.repeat(np.arange(B), lens[perm])
-    row_phone = (np.arange(P) - off[:-1][rep]).astype(np.int32)
-    row_utt = utt_ids[perm][rep].astype(np.int32)
-    seg_lo = off[:-1][rep].astype(np.int32)
-    seg_hi = off[1:][rep].astype(np.int32)
+    off_c = np.zeros(B + 1, dtype=np.int64)
+    off_c[1:] = np.cumsum(lens)                                   # caller-order offsets
+    rep = np.repeat(np.arange(B), lens_p)
+    within = np.arange(P) - off[:-1][rep]
+    gidx = off_c[:-1][perm][rep] + within                         # caller-order flat index of every processed row
 
     def cat(vals, dtype, what):
         if vals is None:
             return None
-        parts = []
-        for i in perm:
-            v = np.asarray(vals[i]).reshape(-1)
-            if v.shape[0] != lens[i]:
-                raise ValueError(f"{what}[{i}] has {v.shape[0]} entries for {lens[i]} phonemes")
-            parts.append(v.astype(dtype))
-        return np.concatenate(parts)
+        if len(vals) != B:
+            raise ValueError(f"{what} has {len(vals)} entries for {B} utterances")
+        try:                                         # fast path: a list of 1-D arrays
+            vl = np.fromiter((v.shape[0] if v.ndim == 1 else -1 for v in vals), dtype=np.int64, count=B)
+            flat = np.concatenate(vals) if (vl >= 0).all() else None
+        except AttributeError:
+            flat = None
+        if flat is None:                             # lists / (N,1) arrays
+            vals = [np.reshape(np.asarray(v), -1) for v in vals]
+            vl = np.fromiter((v.shape[0] for v in vals), dtype=np.int64, count=B)
+            flat = np.concatenate(vals)
+        if (vl != lens).any():
+            i = int(np.nonzero(vl != lens)[0][0])
+            raise ValueError(f"{what}[{i}] has {vl[i]} entries for {lens[i]} phonemes")
+        return flat.astype(dtype, copy=False)[gidx]
 
+    ids = cat(xs, np.int64, "xs")
     dur = cat(durs, np.int32, "durs")
     if dur is not None and (dur < 0).any():
         raise ValueError("negative duration")
     if (f0s is None) != (energies is None):
         raise ValueError("f0 and energy must be forced together (e2e_tts_tacotron2_sa.py:649-651)")
-    return BatchPlan(B, P, perm, ids, off.astype(np.int32), row_utt, row_phone, seg_lo, seg_hi, dur,
+    return BatchPlan(B, P, perm, ids, off.astype(np.int32), utt_ids[perm][rep].astype(np.int32),
+                     within.astype(np.int32), off[:-1][rep].astype(np.int32), off[1:][rep].astype(np.int32), dur,
                      cat(f0s, np.float32, "f0s"), cat(energies, np.float32, "energies"))
 
 
