@@ -207,8 +207,11 @@ def main():
         e1.record()
         return e0, e1, res, eng.stage_events, gathered
 
+    import gc
     for _ in range(args.warmup):
         one_step(False)
+    gc.collect()
+    gc.disable()            # a host GC pause between launches would show up as GPU idle time inside the events
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:

@@ -353,12 +353,18 @@ class Engine:
         for k, a in parts:
             offs[k] = (total, a.shape[0])
             total += (a.shape[0] + 3) // 4 * 4          # keep 16-byte alignment
-        stage = torch.empty((total,), dtype=torch.int32).pin_memory()
+        if getattr(self, "_stage_buf", None) is None or self._stage_buf.numel() < total:
+            self._stage_buf = torch.empty((max(total, 1 << 16),), dtype=torch.int32).pin_memory()   # cached: pinning is slow
+        if getattr(self, "_stage_evt", None) is not None:
+            self._stage_evt.synchronize()               # the previous H2D copy out of this buffer has finished
+        stage = self._stage_buf[:total]
         sn = stage.numpy()
         for k, a in parts:
             o, n = offs[k]
             sn[o:o + n] = a
         dev = stage.to(self.device, non_blocking=True)
+        self._stage_evt = torch.cuda.Event()
+        self._stage_evt.record(torch.cuda.current_stream(self.device))
         v = {k: dev[o:o + n] for k, (o, n) in offs.items()}
         v["ids"] = v["ids"].view(torch.int64)
         for k in ("pitch", "energy"):
