@@ -178,7 +178,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
       for (int tk = 0, tile; (tile = DB_TILE(tk)) >= 0; ++tk) {
         const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
         const uint8_t* himg = reinterpret_cast<const uint8_t*>(p.hn_img) + (size_t)tile * E * 128 * 2;
-        const int zset = tk & 1;
+        const int zset = dm.C > 1 ? (tk & 1) : 0;      // one set is enough without a group (keeps the scratch L2-resident)
         for (int m = 0; m < steps; ++m) {
           const int zp = m & 1;
           const uint8_t* z0cur = zsh + db_z_off(H, zset, zp), *z0new = zsh + db_z_off(H, zset, zp ^ 1);
@@ -307,7 +307,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
       }
       const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
       if (steps == 0) continue;
-      const int zset = tk & 1;
+      const int zset = dm.C > 1 ? (tk & 1) : 0;      // one set is enough without a group (keeps the scratch L2-resident)
       // ---- tile init: x1 of step 0 (the first input frame is zero: prenet.0 sees only its bias) and zero z images
       {
 #pragma unroll 1
