@@ -42,31 +42,89 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
+    In-process NVML (nvidia_ml_py) on a thread: a few light queries every 10 ms. An `nvidia-smi -lms` subprocess
+    was measured to stall kernel launches for tens of ms when a poll (or its start-up) lands inside a timed step;
+    it is only the fallback when NVML cannot be imported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.samples = index, None, [], []
+        self.nvml, self.handle, self.thread, self.run_flag, self.first = None, None, None, False, 0
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.run_flag = True
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
-            self.t.start()
+            self.thread = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _loop(self):
+        n = self.nvml
+        while self.run_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def ready(self):
+        return bool(self.samples) or bool(self.lines) or (self.nvml is None and self.proc is None)
+
+    def mark(self):
+        """Start of the timed region (the sampler is started before the warm-up)."""
+        self.first = len(self.samples) if self.nvml is not None else len(self.lines)
+
     def stop(self):
+        if self.nvml is not None:
+            self.run_flag = False
+            self.thread.join(timeout=1)
+            n = self.nvml
+            sel = self.samples[max(self.first - 1, 0):]
+            names = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r in sel))
+            mhz = [m for m, _ in sel if m > 0]
+            return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sel), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        self.t.join(timeout=2)
+        self.thread.join(timeout=2)
         sm, mx, reasons = [], [], set()
-        for l in self.lines:
+        for l in self.lines[max(self.first - 1, 0):]:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 9:
                 continue
@@ -79,7 +137,7 @@ class ClockSampler:
                     reasons.add(name)
         busy = [s for s in sm if s > 0]
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def workload(args, rank):
@@ -205,17 +263,23 @@ def main():
             with eng.stage("gather"):
                 gathered = fdist.gather_mels(res.out, counts=counts)
         e1.record()
-        return e0, e1, res, eng.stage_events, gathered
+        return e0, e1, None, eng.stage_events, None    # results are dropped: holding K outputs alive would force a
+                                                       # fresh cudaMalloc of the output buffer inside every timed step
 
     import gc
-    for _ in range(args.warmup):
-        one_step(False)
-    gc.collect()
-    gc.disable()            # a host GC pause between launches would show up as GPU idle time inside the events
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        one_step(False)
+    if rank == 0:
+        t_wait = time.time()
+        while not sampler.ready() and time.time() - t_wait < 3.0:
+            time.sleep(0.02)                       # the sampler is up and polling before the timed region starts
+    gc.collect()
+    gc.disable()            # a host GC pause between launches would show up as GPU idle time inside the events
+    barrier()
+    sampler.mark()
     launches0 = eng.launches
     evs = [one_step(True) for _ in range(args.steps)]
     barrier()
@@ -263,6 +327,12 @@ def main():
         dec_flops = 2.0 * macs["decoder_row_step"] * n_frames
         achieved = dec_flops / (dec_ms * 1e-3) / 1e12 if dec_ms > 0 else 0.0
         value = all_frames * args.steps / (total_ms * 1e-3)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "decoder_traffic.json")))
+            traffic = tj.get(f"{args.model}_{args.batch}_{args.precision}", {}).get("bytes")
+        except Exception:
+            pass
         line = {
             "metric": "mel frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -275,7 +345,7 @@ def main():
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": all_launches,
             "roofline": {"kernel": "decoder step loop (fcl_decoder_*), rank 0", "bound": "tensor", "achieved": achieved,
-                         "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"], "traffic": None,
+                         "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"], "traffic": traffic,
                          "peak_source": pk["src"] + " bf16_tflops_sustained", "ms_per_launch": dec_ms,
                          "algorithmic_flops_per_launch": dec_flops,
                          "note": "algorithmic FLOPs = 2 x MAC per useful row-step (reference formulation, nothing hoisted) x frames"},

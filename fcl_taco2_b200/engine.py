@@ -69,9 +69,31 @@ class Engine:
             self.dec_group_sync = torch.zeros((2 * self.n_slots,), dtype=torch.int32, device=self.device)
         self.head_b = {s: float(packed[f"{s}_head_b"][0]) for s in ("dur", "pitch", "energy")}
         self.launches = 0
+        self._arena, self._arena_seq, self._in_pass = [], 0, False
         self.force_group = 0             # decoder group size override (tests); 0 = choose from the tile count
         self.use_encoder_stack = False   # measured: with 256 channels only a 2-stage weight ring fits beside the images
         self.stage_events = None      # when a list: (stage, start_event, stop_event) appended per stage (bench.py)
+
+    # ------------------------------------------------------------------ workspace arena
+    def _buf(self, shape, dtype):
+        """Scratch tensor for the current pass. Inside `run_uploaded` buffers are recycled by call order, so a
+        steady-state pass performs no allocator calls at all (a cudaMalloc/cudaFree hiccup of the caching allocator
+        between launches shows up as GPU idle time); outside a pass (unit tests) it is a plain allocation."""
+        if not self._in_pass:
+            return torch.empty(shape, dtype=dtype, device=self.device)
+        n = 1
+        for d in (shape if isinstance(shape, (tuple, list)) else (shape,)):
+            n *= int(d)
+        i = self._arena_seq
+        self._arena_seq += 1
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        if i >= len(self._arena):
+            self._arena.append(None)
+        cur = self._arena[i]
+        if cur is None or cur.numel() < nbytes:
+            cur = torch.empty((max(nbytes, 256) * 5 // 4 + 255) // 256 * 256, dtype=torch.uint8, device=self.device)
+            self._arena[i] = cur
+        return cur[:nbytes].view(dtype).view(shape)
 
     # ------------------------------------------------------------------ launch helpers
     def _stream(self):
@@ -84,7 +106,7 @@ class Engine:
     def conv_gemm(self, a, w, bias, rows, cin, cout, taps, act, seg=None, gather=None, residual=None, out=None,
                   lda=None, key=None, row_gather=None, out_bf16=False):
         if out is None:
-            out = torch.empty((rows, cout), dtype=torch.float32, device=self.device)
+            out = self._buf((rows, cout), torch.float32)
         if key is not None and key in self.wb:
             wp, ntile, kstage = self.wb[key]
             tm = seg[2] if (seg is not None and taps > 1) else None      # tile maps of the row space
@@ -111,10 +133,10 @@ class Engine:
         if self.precision != "bf16":
             return None
         dev = self.device
-        first = torch.empty((n_segs + 1,), dtype=torch.int32, device=dev)
-        src = torch.empty((max_tiles, 136), dtype=torch.int32, device=dev)
-        dst = torch.empty((max_tiles, 128), dtype=torch.int32, device=dev)
-        count = torch.empty((1,), dtype=torch.int32, device=dev)
+        first = self._buf((n_segs + 1,), torch.int32)
+        src = self._buf((max_tiles, 136), torch.int32)
+        dst = self._buf((max_tiles, 128), torch.int32)
+        count = self._buf((1,), torch.int32)
         self._call("fcl_conv_tiles", _lib.ConvTilesParams(n_segs=n_segs, max_tiles=max_tiles, halo=halo,
                                                           seg_off=dptr(seg_off), seg_first_tile=dptr(first),
                                                           tile_src=dptr(src), tile_dst=dptr(dst), n_tiles=dptr(count)))
@@ -152,14 +174,14 @@ class Engine:
     def _encoder_lstm(self, x, utt_off, n_utts, P):
         hp, w = self.hp, self.w
         E = hp.eunits
-        h = torch.empty((P, E), dtype=torch.float32, device=self.device)
+        h = self._buf((P, E), torch.float32)
         if self.precision == "bf16" and getattr(self, "blstm_whh_bf16", None) is not None:
-            gx = torch.empty((P, 4 * E), dtype=torch.bfloat16, device=self.device)
+            gx = self._buf((P, 4 * E), torch.bfloat16)
             self.conv_gemm(x, None, w["blstm_b"], P, hp.econv_chans, 4 * E, 1, ACT_NONE, key="blstm_wih", out=gx,
                            out_bf16=True)
             tile_utts = 32 if n_utts <= 32 * self.n_slots // 2 else 64 if n_utts <= 64 * self.n_slots // 2 else 128
             n_tiles = (n_utts + tile_utts - 1) // tile_utts
-            c_ws = torch.empty((n_tiles * 2 * (E // 2) * 128,), dtype=torch.float32, device=self.device)
+            c_ws = self._buf((n_tiles * 2 * (E // 2) * 128,), torch.float32)
             self._call("fcl_bilstm_bf16", _lib.BiLstmBf16Params(n_utts=n_utts, hidden=E // 2, tile_utts=tile_utts,
                                                                 utt_off=dptr(utt_off),
                                                                 gx=dptr(gx), whh_packed=dptr(self.blstm_whh_bf16),
@@ -179,15 +201,15 @@ class Engine:
                            key=f"{name}_conv0")
         self.layernorm(x, w[f"{name}_ln0_g"], w[f"{name}_ln0_b"], y=x)
         x = self.conv_gemm(x, w[f"{name}_conv1_w"], w[f"{name}_conv1_b"], P, C, C, 3, ACT_RELU, seg=seg, key=f"{name}_conv1")
-        head = torch.empty((P,), dtype=torch.float32, device=self.device)
-        dur = torch.empty((P,), dtype=torch.int32, device=self.device) if want_dur else None
+        head = self._buf((P,), torch.float32)
+        dur = self._buf((P,), torch.int32) if want_dur else None
         self.layernorm(x, w[f"{name}_ln1_g"], w[f"{name}_ln1_b"], head_w=w[f"{name}_head_w"],
                        head_b=self.head_b[name], head_out=head, dur_out=dur)
         return head, dur
 
     def embed_add(self, h, pitch, energy, seg):
         hp, w = self.hp, self.w
-        hn = torch.empty_like(h)
+        hn = self._buf(tuple(h.shape), torch.float32)
         p = _lib.EmbedAddParams(rows=h.shape[0], chans=hp.eunits, taps=hp.embed_kernel, h=dptr(h), pitch=dptr(pitch),
                                 energy=dptr(energy), seg_lo=dptr(seg[0]), seg_hi=dptr(seg[1]), wp=dptr(w["pemb_w"]),
                                 bp=dptr(w["pemb_b"]), we=dptr(w["eemb_w"]), be=dptr(w["eemb_b"]), hn=dptr(hn))
@@ -197,10 +219,10 @@ class Engine:
     def len_reg_scan(self, dur, utt_off, n_utts):
         P = dur.shape[0]
         dev = self.device
-        frame_off = torch.empty((P + 1,), dtype=torch.int32, device=dev)
-        utt_frame_off = torch.empty((n_utts + 1,), dtype=torch.int32, device=dev)
-        order = torch.empty((P,), dtype=torch.int32, device=dev)
-        totals = torch.empty((2,), dtype=torch.int32, device=dev)
+        frame_off = self._buf((P + 1,), torch.int32)
+        utt_frame_off = self._buf((n_utts + 1,), torch.int32)
+        order = self._buf((P,), torch.int32)
+        totals = self._buf((2,), torch.int32)
         p = _lib.LenRegParams(n_rows=P, n_utts=n_utts, dur=dptr(dur), utt_off=dptr(utt_off), frame_off=dptr(frame_off),
                               utt_frame_off=dptr(utt_frame_off), order=dptr(order), totals=dptr(totals))
         self._call("fcl_len_reg_scan", p)
@@ -208,8 +230,8 @@ class Engine:
 
     def frame_map(self, frame_off, utt_frame_off, n_rows, n_utts, n_frames, want_position=False):
         dev = self.device
-        buf = torch.empty((4, max(n_frames, 1)), dtype=torch.int32, device=dev)
-        pos = torch.empty((max(n_frames, 1),), dtype=torch.float32, device=dev) if want_position else None
+        buf = self._buf((4, max(n_frames, 1)), torch.int32)
+        pos = self._buf((max(n_frames, 1),), torch.float32) if want_position else None
         p = _lib.FrameMapParams(n_rows=n_rows, n_utts=n_utts, n_frames=n_frames, frame_off=dptr(frame_off),
                                 utt_frame_off=dptr(utt_frame_off), frame_row=dptr(buf[0]), frame_step=dptr(buf[1]),
                                 frame_seg_lo=dptr(buf[2]), frame_seg_hi=dptr(buf[3]), position=dptr(pos))
@@ -226,8 +248,8 @@ class Engine:
         with self.stage("decoder_hoist"):
             g0h = self.conv_gemm(hn, w["dec_g0h_w"], w["dec_g0h_b"], P, E, 4 * H, 1, ACT_NONE)
             y0h = self.conv_gemm(hn, w["dec_y0h_w"], None, P, E, O, 1, ACT_NONE)
-        cstate = torch.empty((2, P, H), dtype=torch.float32, device=self.device)
-        before = torch.empty((max(n_frames, 1), O), dtype=torch.float32, device=self.device)
+        cstate = self._buf((2, P, H), torch.float32)
+        before = self._buf((max(n_frames, 1), O), torch.float32)
         if tile_rows is None:
             tile_rows = 32 if H <= 512 else 16
         p = _lib.DecoderParams(n_rows=P, eunits=E, dunits=H, prenet_units=hp.prenet_units, odim=O, order=dptr(order),
@@ -248,7 +270,7 @@ class Engine:
         P, E, H, O = hn.shape[0], hp.eunits, hp.dunits, hp.odim
         n_tiles = (P + 127) // 128
         with self.stage("decoder_hoist"):
-            hn_img = torch.empty((n_tiles * 128 * E,), dtype=torch.bfloat16, device=self.device)
+            hn_img = self._buf((n_tiles * 128 * E,), torch.bfloat16)
             self._call("fcl_pack_rows_bf16", _lib.PackRowsParams(n_rows=P, cols=E, src=dptr(hn), ld=E, order=dptr(order),
                                                                  dst=dptr(hn_img)))
             # few tiles (small batch / one utterance): groups of CTAs split each tile's gate columns so that every SM
@@ -261,11 +283,11 @@ class Engine:
             group = self.force_group or group
             n_groups = min(self.n_slots // group, n_tiles)
             n_slots = n_groups * group
-            sched = torch.empty((2, n_tiles), dtype=torch.int32, device=self.device)
+            sched = self._buf((2, n_tiles), torch.int32)
             self._call("fcl_decoder_schedule", _lib.DecoderScheduleParams(n_rows=P, n_tiles=n_tiles, n_slots=n_groups,
                                                                           order=dptr(order), dur=dptr(dur),
                                                                           tile_slot=dptr(sched[0]), tile_rank=dptr(sched[1])))
-        before = torch.empty((max(n_frames, 1), O), dtype=torch.float32, device=self.device)
+        before = self._buf((max(n_frames, 1), O), torch.float32)
         trace = getattr(self, "dec_trace", None)
         p = _lib.DecoderBf16Params(n_rows=P, n_tiles=n_tiles, n_slots=n_slots, eunits=E, dunits=H,
                                    prenet_units=hp.prenet_units, odim=O, order=dptr(order), dur=dptr(dur),
@@ -284,7 +306,7 @@ class Engine:
         return before
 
     def conv_stack(self, keys, acts, x, ld_in, rows, seg_off, n_segs, max_len_sum_tiles, taps=5, gather=None,
-                   residual=None, wkeys=None):
+                   residual=None, wkeys=None, final=False):
         """Fused conv stack (fcl_conv_stack_bf16) over the layers `keys`; returns None when the stack does not
         fit on chip (caller falls back to layer-by-layer fcl_conv_gemm_bf16)."""
         L = len(keys)
@@ -306,13 +328,14 @@ class Engine:
             return None
         dev = self.device
         max_tiles = max_len_sum_tiles(stride)
-        tiles = torch.empty((max_tiles, 4), dtype=torch.int32, device=dev)
-        count = torch.empty((1,), dtype=torch.int32, device=dev)
+        tiles = self._buf((max_tiles, 4), torch.int32)
+        count = self._buf((1,), torch.int32)
         self._call("fcl_conv_stack_tiles", _lib.ConvStackTilesParams(n_segs=n_segs, max_tiles=max_tiles, stride=stride,
                                                                      seg_off=dptr(seg_off), tiles=dptr(tiles),
                                                                      n_tiles=dptr(count)))
         cout_last = layers[L - 1].cout
-        out = torch.empty((rows, cout_last), dtype=torch.float32, device=dev)
+        out = torch.empty((rows, cout_last), dtype=torch.float32, device=dev) if final else \
+            self._buf((rows, cout_last), torch.float32)
         self._call("fcl_conv_stack_bf16", _lib.ConvStackParams(n_layers=L, taps=taps, layers=layers, in_=dptr(x), ld_in=ld_in,
                                                                in_channels=in_channels, b_stages=0, gather=dptr(gather), tiles=dptr(tiles), n_tiles_dev=dptr(count),
                                                                n_tiles=max_tiles, residual=dptr(residual), ldr=cout_last,
@@ -326,6 +349,7 @@ class Engine:
             utt_frame_off, n_utts = fseg[3]
             out = self.conv_stack([f"post_conv{l}" for l in range(5)], [ACT_TANH] * 4 + [ACT_NONE], before, O, n_frames,
                                   utt_frame_off, n_utts, lambda s: (n_frames + s - 1) // s + n_utts, residual=before,
+                                  final=True,
                                   wkeys=[f"post_stack{l}" if f"post_stack{l}" in self.wb else f"post_conv{l}"
                                          for l in range(5)])
             if out is not None:
@@ -335,8 +359,9 @@ class Engine:
         for l in (1, 2, 3):
             x = self.conv_gemm(x, w[f"post_conv{l}_w"], w[f"post_conv{l}_b"], n_frames, C, C, 5, ACT_TANH, seg=fseg,
                                key=f"post_conv{l}")
+        final = torch.empty((n_frames, O), dtype=torch.float32, device=self.device)     # returned to the caller
         return self.conv_gemm(x, w["post_conv4_w"], w["post_conv4_b"], n_frames, C, O, 5, ACT_NONE, seg=fseg,
-                              residual=before, key="post_conv4")
+                              residual=before, key="post_conv4", out=final)
 
     # ------------------------------------------------------------------ whole pass
     def upload(self, plan: BatchPlan):
@@ -400,6 +425,13 @@ class Engine:
     def run_uploaded(self, plan: BatchPlan, d: dict, zoneout: float, dropout_p: float, dropout_seed: int,
                      extras: bool = False, tile_rows=None, h2d: int = 0) -> BatchResult:
         """The pass proper, inputs already resident on the device (`d` from `upload`)."""
+        self._arena_seq, self._in_pass = 0, not extras     # extras (tests) keep intermediates: no recycling
+        try:
+            return self._run_uploaded(plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d)
+        finally:
+            self._in_pass = False
+
+    def _run_uploaded(self, plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d):
         hp = self.hp
         B, P = plan.n_utts, plan.n_rows
         ex = {"h2d_bytes": h2d}
