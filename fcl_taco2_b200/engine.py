@@ -22,6 +22,9 @@ from .hparams import HParams
 from .plan import BatchPlan
 
 
+_ELEM_SIZE = {torch.float32: 4, torch.int32: 4, torch.bfloat16: 2, torch.int64: 8, torch.uint8: 1}
+
+
 @dataclass
 class BatchResult:
     out: torch.Tensor                  # (F, odim) fp32, frames of all utterances in processing order
@@ -69,7 +72,8 @@ class Engine:
             self.dec_group_sync = torch.zeros((2 * self.n_slots,), dtype=torch.int32, device=self.device)
         self.head_b = {s: float(packed[f"{s}_head_b"][0]) for s in ("dur", "pitch", "energy")}
         self.launches = 0
-        self._arena, self._arena_seq, self._in_pass = [], 0, False
+        self._arena, self._arena_views, self._arena_seq, self._in_pass = [], [], 0, False
+        self._stream_handle = None
         self.force_group = 0             # decoder group size override (tests); 0 = choose from the tile count
         self.use_encoder_stack = False   # measured: with 256 channels only a 2-stage weight ring fits beside the images
         self.stage_events = None      # when a list: (stage, start_event, stop_event) appended per stage (bench.py)
@@ -81,23 +85,31 @@ class Engine:
         between launches shows up as GPU idle time); outside a pass (unit tests) it is a plain allocation."""
         if not self._in_pass:
             return torch.empty(shape, dtype=dtype, device=self.device)
+        i = self._arena_seq
+        self._arena_seq += 1
+        if i < len(self._arena_views):
+            hit = self._arena_views[i]
+            if hit is not None and hit[0] == shape and hit[1] is dtype:
+                return hit[2]                                   # same shape as in the previous pass: no tensor ops at all
+        else:
+            self._arena.append(None)
+            self._arena_views.append(None)
         n = 1
         for d in (shape if isinstance(shape, (tuple, list)) else (shape,)):
             n *= int(d)
-        i = self._arena_seq
-        self._arena_seq += 1
-        nbytes = n * torch.empty((), dtype=dtype).element_size()
-        if i >= len(self._arena):
-            self._arena.append(None)
+        nbytes = n * _ELEM_SIZE[dtype]
         cur = self._arena[i]
         if cur is None or cur.numel() < nbytes:
             cur = torch.empty((max(nbytes, 256) * 5 // 4 + 255) // 256 * 256, dtype=torch.uint8, device=self.device)
             self._arena[i] = cur
-        return cur[:nbytes].view(dtype).view(shape)
+        view = cur[:nbytes].view(dtype).view(shape)
+        self._arena_views[i] = (shape, dtype, view)
+        return view
 
     # ------------------------------------------------------------------ launch helpers
     def _stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
+        h = self._stream_handle                       # cached for the duration of a pass (set by _run_uploaded)
+        return h if h is not None else torch.cuda.current_stream(self.device).cuda_stream
 
     def _call(self, name, params):
         _lib.call(name, params, self._stream())
@@ -239,12 +251,12 @@ class Engine:
         return buf, pos
 
     def decoder(self, hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p, dropout_seed,
-                tile_rows=None):
+                tile_rows=None, schedule=None):
         hp, w = self.hp, self.w
         P, E, H, O = hn.shape[0], hp.eunits, hp.dunits, hp.odim
         if self.precision == "bf16" and self.bf16_decoder:
             return self.decoder_bf16(hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p,
-                                     dropout_seed)
+                                     dropout_seed, schedule)
         with self.stage("decoder_hoist"):
             g0h = self.conv_gemm(hn, w["dec_g0h_w"], w["dec_g0h_b"], P, E, 4 * H, 1, ACT_NONE)
             y0h = self.conv_gemm(hn, w["dec_y0h_w"], None, P, E, O, 1, ACT_NONE)
@@ -263,7 +275,29 @@ class Engine:
             self._call("fcl_decoder_f32", p)
         return before
 
-    def decoder_bf16(self, hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p, dropout_seed):
+    def decoder_schedule(self, order, dur, P):
+        """Group size + longest-processing-time tile assignment of the tensor-core decoder (integer work that only
+        depends on the durations: runs on the side stream, off the critical path)."""
+        H = self.hp.dunits
+        n_tiles = (P + 127) // 128
+        # few tiles (small batch / one utterance): groups of CTAs split each tile's gate columns so that every SM
+        # streams only its share of the LSTM weights
+        gate_chunks = 4 * H // 256
+        group = 1
+        for g in range(2, min(gate_chunks, 16, self.n_slots // max(n_tiles, 1)) + 1):
+            if -(-gate_chunks // g) < -(-gate_chunks // group):      # fewer chunks per CTA
+                group = g
+        group = self.force_group or group
+        n_groups = min(self.n_slots // group, n_tiles)
+        n_slots = n_groups * group
+        sched = self._buf((2, n_tiles), torch.int32)
+        self._call("fcl_decoder_schedule", _lib.DecoderScheduleParams(n_rows=P, n_tiles=n_tiles, n_slots=n_groups,
+                                                                      order=dptr(order), dur=dptr(dur),
+                                                                      tile_slot=dptr(sched[0]), tile_rank=dptr(sched[1])))
+        return group, n_groups, n_slots, sched
+
+    def decoder_bf16(self, hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p, dropout_seed,
+                     schedule=None):
         """Tensor-core decoder: h packed as a bf16 operand image in duration-sorted tile order, then the
         persistent tcgen05 loop."""
         hp, w = self.hp, self.w
@@ -273,20 +307,7 @@ class Engine:
             hn_img = self._buf((n_tiles * 128 * E,), torch.bfloat16)
             self._call("fcl_pack_rows_bf16", _lib.PackRowsParams(n_rows=P, cols=E, src=dptr(hn), ld=E, order=dptr(order),
                                                                  dst=dptr(hn_img)))
-            # few tiles (small batch / one utterance): groups of CTAs split each tile's gate columns so that every SM
-            # streams only its share of the LSTM weights
-            gate_chunks = 4 * H // 256
-            group = 1
-            for g in range(2, min(gate_chunks, 16, self.n_slots // max(n_tiles, 1)) + 1):
-                if -(-gate_chunks // g) < -(-gate_chunks // group):      # fewer chunks per CTA
-                    group = g
-            group = self.force_group or group
-            n_groups = min(self.n_slots // group, n_tiles)
-            n_slots = n_groups * group
-            sched = self._buf((2, n_tiles), torch.int32)
-            self._call("fcl_decoder_schedule", _lib.DecoderScheduleParams(n_rows=P, n_tiles=n_tiles, n_slots=n_groups,
-                                                                          order=dptr(order), dur=dptr(dur),
-                                                                          tile_slot=dptr(sched[0]), tile_rank=dptr(sched[1])))
+        group, n_groups, n_slots, sched = schedule if schedule is not None else self.decoder_schedule(order, dur, P)
         before = self._buf((max(n_frames, 1), O), torch.float32)
         trace = getattr(self, "dec_trace", None)
         p = _lib.DecoderBf16Params(n_rows=P, n_tiles=n_tiles, n_slots=n_slots, eunits=E, dunits=H,
@@ -430,16 +451,53 @@ class Engine:
             return self._run_uploaded(plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d)
         finally:
             self._in_pass = False
+            self._stream_handle = None
 
     def _run_uploaded(self, plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d):
         hp = self.hp
         B, P = plan.n_utts, plan.n_rows
         ex = {"h2d_bytes": h2d}
         lens = np.diff(plan.utt_off.astype(np.int64))
+        need_pred_dur = plan.dur is None
+        main = torch.cuda.current_stream(self.device)
+        self._stream_handle = main.cuda_stream
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        side = self._side
+
+        def length_regulation(dur, F):
+            """Integer work that depends only on the durations: scan / sort, frame map, postnet tiles, decoder tile
+            schedule. With forced durations it runs on a side stream concurrently with the encoder and predictors."""
+            with self.stage("len_reg"):
+                frame_off, utt_frame_off, order, totals = self.len_reg_scan(dur, d["utt_off"], B)
+            sched = self.decoder_schedule(order, dur, P) if self.precision == "bf16" and self.bf16_decoder else None
+            fmap = pos = ftiles = None
+            if F is not None:
+                with self.stage("frame_map"):
+                    fmap, pos = self.frame_map(frame_off, utt_frame_off, P, B, F, want_position=extras)
+                    ftiles = self.conv_tiles(utt_frame_off, B, (F + 127) // 128 + B)
+            return frame_off, utt_frame_off, order, totals, sched, fmap, pos, ftiles
+
+        lr = None
+        if not need_pred_dur:
+            if (plan.dur == 0).any():
+                raise ValueError("zero durations are outside the reference's working domain "
+                                 "(nets/modules/decoder_sa.py:575)")
+            per_utt = np.add.reduceat(np.minimum(plan.dur, _lib.MAX_DURATION).astype(np.int64), plan.utt_off[:-1].astype(np.int64))
+            ufo = np.concatenate([[0], np.cumsum(per_utt)])
+            F = int(ufo[-1])
+            use_side = P >= 4096                           # tiny batches: the cross-stream hand-over costs more than it hides
+            if use_side:
+                side.wait_stream(main)                     # inputs uploaded, previous pass finished with the arena
+                with torch.cuda.stream(side):
+                    self._stream_handle = side.cuda_stream
+                    lr = length_regulation(d["dur"], F)
+                self._stream_handle = main.cuda_stream
+            else:
+                lr = length_regulation(d["dur"], F)
         with self.stage("encoder"):
             seg = (d["seg_lo"], d["seg_hi"], self.conv_tiles(d["utt_off"], B, int(((lens + 127) // 128).sum())))
             h = self.encoder(d["ids"], d["utt_off"], seg, B, lens=lens)
-        need_pred_dur = plan.dur is None
         dlog = dur_pred = None
         with self.stage("predictors"):
             if need_pred_dur or extras:
@@ -451,26 +509,22 @@ class Engine:
             else:
                 pitch, energy = d["pitch"], d["energy"]
             hn = self.embed_add(h, pitch, energy, seg)
-        with self.stage("len_reg"):
-            frame_off, utt_frame_off, order, totals = self.len_reg_scan(dur, d["utt_off"], B)
         if need_pred_dur:
+            frame_off, utt_frame_off, order, totals, sched, _, _, _ = length_regulation(dur, None)
             host = torch.cat([totals, utt_frame_off]).cpu().numpy()      # the one data-dependent D2H sync
             F, ufo = int(host[0]), host[2:].astype(np.int64)
             if int((dur == 0).sum()) != 0:
                 raise ValueError("predicted zero durations: outside the reference's working domain "
                                  "(nets/modules/decoder_sa.py:575); pass dur=")
+            with self.stage("frame_map"):
+                fmap, pos = self.frame_map(frame_off, utt_frame_off, P, B, F, want_position=extras)
+                ftiles = self.conv_tiles(utt_frame_off, B, (F + 127) // 128 + B)
         else:
-            if (plan.dur == 0).any():
-                raise ValueError("zero durations are outside the reference's working domain "
-                                 "(nets/modules/decoder_sa.py:575)")
-            per_utt = np.add.reduceat(np.minimum(plan.dur, _lib.MAX_DURATION).astype(np.int64), plan.utt_off[:-1].astype(np.int64))
-            ufo = np.concatenate([[0], np.cumsum(per_utt)])
-            F = int(ufo[-1])
+            frame_off, utt_frame_off, order, totals, sched, fmap, pos, ftiles = lr
+            if use_side:
+                main.wait_stream(side)
         before = self.decoder(hn, dur, frame_off, order, d["row_utt"], d["row_phone"], F, zoneout, dropout_p,
-                              dropout_seed, tile_rows)
-        with self.stage("frame_map"):
-            fmap, pos = self.frame_map(frame_off, utt_frame_off, P, B, F, want_position=extras)
-            ftiles = self.conv_tiles(utt_frame_off, B, (F + 127) // 128 + B)
+                              dropout_seed, tile_rows, schedule=sched)
         with self.stage("postnet"):
             out = self.postnet(before, (fmap[2], fmap[3], ftiles, (utt_frame_off, B)), F)
         if extras:
