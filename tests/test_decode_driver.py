@@ -67,7 +67,7 @@ def test_decode_end_to_end(tmp_path, monkeypatch):
     """Random-init duration predictors emit zeros (the reference asserts on that too), so bias the duration head."""
     exp, xs, sd = _make_exp(tmp_path, snapshot=False)
     sd = dict(sd)
-    sd["duration_predictor.linear.bias"] = torch.tensor([1.6])
+    sd["duration_predictor.linear.bias"] = torch.tensor([2.5])           # durations ~ exp(2.5 +- 1) - 1: all >= 1
     torch.save(sd, exp / "snapshot.ep.100")
     monkeypatch.chdir(tmp_path)
     args = D.get_parser().parse_args(["--out", str(tmp_path / "decode" / "feats"), "--json", str(tmp_path / "test_data.1.json"),
