@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -103,7 +103,7 @@ class BiLstmBf16Params(C.Structure):
 
 
 class DecoderScheduleParams(C.Structure):
-    _fields_ = [("n_rows", i32), ("n_tiles", i32), ("n_slots", i32), ("order", ptr), ("dur", ptr),
+    _fields_ = [("n_rows", i32), ("n_tiles", i32), ("n_slots", i32), ("unit_rows", i32), ("order", ptr), ("dur", ptr),
                 ("tile_slot", ptr), ("tile_rank", ptr)]
 
 
@@ -129,6 +129,7 @@ ENTRY_POINTS = {
     "fcl_bilstm_bf16": BiLstmBf16Params,
     "fcl_conv_tiles": ConvTilesParams,
     "fcl_decoder_schedule": DecoderScheduleParams,
+    "fcl_decoder_bf16_pair": DecoderBf16Params,
     "fcl_conv_stack_tiles": ConvStackTilesParams,
     "fcl_conv_stack_bf16": ConvStackParams,
 }

@@ -1,41 +1,27 @@
-// K4 (tensor-core path): persistent decoder step loop on tcgen05.
-// Reference: nets/modules/decoder_sa.py:577-617 (loop), :146-158 (Prenet, always-on dropout),
-// :63-96 (ZoneOutCell around torch.nn.LSTMCell), :398 (feat_out), fused with the ragged gather :619-630.
-//
-// One CTA owns a tile of 128 duration-sorted phoneme rows for all of their steps (rows are independent, so
-// no inter-CTA communication exists). Per step it runs four dependent GEMM phases on the tensor cores
-//   P1 prenet.1: x1 (K = 256) x 256
-//   L0 gates of cell 0: [h | z0 | x2] (K = E + H + 256) x 4H      L1 gates of cell 1: [z1 | z0'] (K = 2H) x 4H
-//   FP [h | z1'] (K = E + H) x {80 feat_out columns ; 256 columns of prenet.0 composed with feat_out}
-// Two algebraic rearrangements keep the dependency chain short: (1) feat_out has no activation, so
-// prenet.0(y) = relu(y Wp0^T + b) = relu([z1'|h] (Wfeat^T Wp0^T) + b): the next step's prenet.0 shares the
-// operand (and the phase) of feat_out; (2) inside every phase the K-slices that are already known (h, the
-// previous step's z) come first and the slice produced by the previous phase comes last, so the MMAs of a
-// phase start while the previous phase's epilogue is still running.
-// All GEMMs use bf16 operands, fp32 accumulators in TMEM (two 256-column buffers: the epilogue of chunk j overlaps
-// the MMAs of chunk j+1), fp32 cell state. The encoder state h of the tile is a K-slice of the A operand
-// (it is NOT hoisted into a per-row fp32 table: re-reading such a table every step made the epilogue
-// latency-bound on HBM). Weights (bf16, pre-tiled as UMMA core matrices, in consumption order) and the
-// activation operands stream through a 4-stage shared-memory ring with cp.async.bulk; the activation
-// operands of a tile (x0,x1,x2,z0,z1 as bf16 core-matrix images) live in a per-CTA global scratch that stays
-// L2-resident, written by the epilogue warps and re-read by the bulk copies (generic->async proxy fence +
-// mbarrier hand-over).
-//
-// Warp roles (640 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-19 = epilogue (TMEM lane quarter = warp % 4; column quarter = (warp - 4) / 4: 64 of a chunk's 256
-// columns). Gate columns are interleaved (unit*4 + {i,f,g,o}) so one thread owns whole LSTM cells; the old
-// cell state / old z of the NEXT chunk are requested before the current chunk is computed.
+// K4, cta_group::2 variant: a PAIR of CTAs (two SMs of one TPC, launched as a 2-CTA cluster) processes two
+// 128-row tiles with ONE M=256 tcgen05.mma stream. Same phases, epilogue and scratch layout as decoder_bf16.cu
+// (see there for the algorithm and the reference lines); what changes is the operand path:
+//   * every weight stage is split along N: each CTA loads only ITS half (128 of 256 columns) and the tensor cores
+//     of both SMs consume both halves, so per SM a stage is 16 KB of A + 16 KB of B instead of 16 + 32 KB -- the
+//     single-CTA kernel is bound by shared-memory bandwidth in the MMA phases (every operand byte is written once
+//     by the bulk copy and read once by the MMA: 96 KB per 512-cycle stage against 128 B/clk);
+//   * the leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 for both; tcgen05.commit multicasts the
+//     "stage free" / "accumulator ready" arrivals to both CTAs' mbarriers;
+//   * the peer tells the leader "my half of stage s has landed" and "my epilogue drained accumulator b" with remote
+//     mbarrier arrivals (mapa + mbarrier.arrive.shared::cluster) from two relay threads.
+// The pair walks SUPER-tiles (tiles 2j, 2j+1 of the duration-sorted order) for the step count of the longer one.
 #include "common.cuh"
 #include "umma.cuh"
 
 namespace fcl {
+namespace pair {
 using namespace umma;
 
 constexpr int kDbThreads = 640;
-constexpr int kDbStages = 4;
+constexpr int kDbStages = 6;
 constexpr uint32_t kABytes = 128u * 64u * 2u;           // one A stage: 128 rows x 64 k (bf16)
-constexpr uint32_t kBBytesMax = 256u * 64u * 2u;        // one B stage: up to 256 cols x 64 k
-constexpr uint32_t kStageBytes = kABytes + kBBytesMax;  // 48 KB
+constexpr uint32_t kBBytesMax = 128u * 64u * 2u;        // one B stage of THIS CTA: half of the 256 columns x 64 k
+constexpr uint32_t kStageBytes = kABytes + kBBytesMax;  // 32 KB
 constexpr int kEpiThreads = 512;
 constexpr int kDbMaxTilesPerCta = 512;
 
@@ -43,6 +29,8 @@ struct DbShared {
   uint64_t full[kDbStages], empty[kDbStages];
   uint64_t tmem_full[2], tmem_empty[2];
   uint64_t a_ready[4];        // x1, x2, z0', z1' operand images complete (epilogue -> producer)
+  uint64_t peer_full[kDbStages];   // leader only: the peer CTA's half of stage s has landed (remote arrive)
+  uint64_t peer_tmem_empty[2];     // leader only: the peer's epilogue drained accumulator buffer b (remote arrive)
   uint32_t tmem_base;
   int n_my_tiles;
   int my_tiles[kDbMaxTilesPerCta];
@@ -73,6 +61,40 @@ __device__ __forceinline__ void db_trace(const FclDecoderBf16Params& p, int id) 
       p.trace[3 + 2 * n] = clock64();
     }
   }
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (count 1) on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[128 rows per CTA] * B[N/2 columns per CTA]^T ; issued by ONE thread of the leader CTA
+__device__ __forceinline__ void mma2_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// both CTAs' mbarriers (same offset) get one arrival when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void mma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
 struct DbDims {
@@ -134,23 +156,25 @@ __device__ __forceinline__ void prenet_store16(const float* v, const float* __re
 }
 
 __global__ void __launch_bounds__(kDbThreads, 1)
-decoder_bf16_kernel(FclDecoderBf16Params p) {
+decoder_bf16_pair_kernel(FclDecoderBf16Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ DbShared sh;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.dunits, U = p.prenet_units, O = p.odim, E = p.eunits;
   DbDims dm;
   dm.kU = U / 64; dm.kH = H / 64; dm.kE = E / 64; dm.gate_chunks = 4 * H / 256;
-  dm.C = p.group; dm.cr = (int)blockIdx.x % p.group;
-  const int grp = (int)blockIdx.x / p.group;
+  dm.C = 1; dm.cr = 0;                                  // pair mode: every CTA owns all chunks of ITS tile
+  const uint32_t rank = cluster_ctarank();              // 0 = leader (issues the MMAs), 1 = peer
+  const int grp = (int)blockIdx.x >> 1;                 // the pair = one schedule slot; it walks SUPER-tiles (2 tiles)
   uint8_t* act = reinterpret_cast<uint8_t*>(p.act_priv) + (size_t)blockIdx.x * db_priv_bytes(U);          // x1 | x2
-  uint8_t* zsh = reinterpret_cast<uint8_t*>(p.act_shared) + (size_t)grp * db_shared_bytes(H);             // z images
+  uint8_t* zsh = reinterpret_cast<uint8_t*>(p.act_shared) + (size_t)blockIdx.x * db_shared_bytes(H);      // z images
   float* cws = p.c_ws + (size_t)blockIdx.x * 2 * H * 128;
 
   // this CTA's tile list (longest-processing-time schedule)
   if (tid == 0) sh.n_my_tiles = 0;
   __syncthreads();
-  for (int t = tid; t < p.n_tiles; t += kDbThreads) {
+  const int n_super = (p.n_tiles + 1) >> 1;
+  for (int t = tid; t < n_super; t += kDbThreads) {
     if (p.tile_slot[t] == grp) {
       const int k = p.tile_rank[t];
       if (k < kDbMaxTilesPerCta) { sh.my_tiles[k] = t; atomicMax(&sh.n_my_tiles, k + 1); }
@@ -160,14 +184,18 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
     for (int s = 0; s < kDbStages; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&sh.tmem_full[b], 1); mbar_init(&sh.tmem_empty[b], kEpiThreads); }
     for (int i = 0; i < 4; ++i) mbar_init(&sh.a_ready[i], kEpiThreads);
+    for (int s = 0; s < kDbStages; ++s) mbar_init(&sh.peer_full[s], 1);
+    for (int b = 0; b < 2; ++b) mbar_init(&sh.peer_tmem_empty[b], 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&sh.tmem_base, 512);
+  cluster_sync_all();                                   // barriers of both CTAs initialised before any remote arrive
+  if (warp == 2) tmem_alloc2(&sh.tmem_base, 512);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
-  const uint32_t b_bytes_wide = 256u * 64u * 2u, b_bytes_feat = (uint32_t)O * 64u * 2u;
+  // per-CTA halves: 128 of the 256 gate/prenet columns, 64 of the feat_out columns (odim zero-padded to 128)
+  const uint32_t b_bytes_wide = 128u * 64u * 2u, b_bytes_feat = 64u * 64u * 2u;
 
   if (warp == 0) {
     // ================================================================ producer
@@ -175,8 +203,9 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
       uint32_t stage = 0, sphase = 0;                 // ring position / parity
       uint32_t rdy[4] = {0, 0, 0, 0};                 // parity of each a_ready barrier
       int sync_ev[2] = {0, 0};                        // group barriers passed so far (z0', z1')
-      for (int tk = 0, tile; (tile = DB_TILE(tk)) >= 0; ++tk) {
-        const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
+      for (int tk = 0, st; (st = DB_TILE(tk)) >= 0; ++tk) {
+        const int steps = min(max(p.dur[p.order[(size_t)st * 256]], 0), FCL_MAX_DURATION);   // the pair runs the longer tile's steps
+        const int tile = min(2 * st + (int)rank, p.n_tiles - 1);    // an odd tile count leaves the last peer a dummy (masked) tile
         const uint8_t* himg = reinterpret_cast<const uint8_t*>(p.hn_img) + (size_t)tile * E * 128 * 2;
         const int zset = dm.C > 1 ? (tk & 1) : 0;      // one set is enough without a group (keeps the scratch L2-resident)
         for (int m = 0; m < steps; ++m) {
@@ -198,7 +227,9 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
             for (int c = 0; c < nch; ++c) {
               if (!dm.owns(phase, c)) continue;
               const uint32_t bb = (phase == 3 && c == 0) ? b_bytes_feat : b_bytes_wide;
-              const uint8_t* wptr = reinterpret_cast<const uint8_t*>(p.w_stream) + dm.w_off(phase, c, b_bytes_wide, b_bytes_feat);
+              // stage blocks hold both halves back to back: [rank 0 half][rank 1 half]
+              const uint8_t* wptr = reinterpret_cast<const uint8_t*>(p.w_stream) +
+                                    dm.w_off(phase, c, 2 * b_bytes_wide, 2 * b_bytes_feat) + (size_t)rank * bb;
               for (int ks = 0; ks < kst; ++ks) {
                 if (!waited && ks == late) {           // operand written by the previous phase's epilogue(s)
                   waited = true;
@@ -222,10 +253,10 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
                 else asrc = ks < dm.kE ? himg + (size_t)ks * kABytes : z1new + (size_t)(ks - dm.kE) * kABytes;
                 mbar_wait(&sh.empty[stage], sphase ^ 1u);
                 mbar_arrive_expect_tx(&sh.full[stage], kABytes + bb);
-                uint8_t* st = smem + (size_t)stage * kStageBytes;
-                bulk_g2s(st, asrc, kABytes, &sh.full[stage]);
-                bulk_g2s(st + kABytes, wptr, bb, &sh.full[stage]);
-                wptr += bb;
+                uint8_t* stg = smem + (size_t)stage * kStageBytes;
+                bulk_g2s(stg, asrc, kABytes, &sh.full[stage]);
+                bulk_g2s(stg + kABytes, wptr, bb, &sh.full[stage]);
+                wptr += 2 * bb;
                 if (++stage == kDbStages) { stage = 0; sphase ^= 1u; }
               }
             }
@@ -239,44 +270,74 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ================================================================ MMA issuer
+    // ================================================================ MMA issuer (leader) / stage-full relay (peer)
     if (elect_one()) {
       uint32_t stage = 0, sphase = 0;
       uint32_t chunk_ctr = 0;                          // accumulator buffer = chunk_ctr & 1
-      const uint32_t idesc_wide = idesc_bf16_f32(128u, 256u), idesc_feat = idesc_bf16_f32(128u, (uint32_t)O);
-      for (int tk = 0, tile; (tile = DB_TILE(tk)) >= 0; ++tk) {
-        const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
+      const uint32_t idesc_wide = idesc_bf16_f32(256u, 256u), idesc_feat = idesc_bf16_f32(256u, 128u);
+      for (int tk = 0, st; (st = DB_TILE(tk)) >= 0; ++tk) {
+        const int steps = min(max(p.dur[p.order[(size_t)st * 256]], 0), FCL_MAX_DURATION);
         for (int m = 0; m < steps; ++m) {
           for (int phase = 0; phase < 4; ++phase) {
             const int nch = dm.nchunks(phase, m + 1 == steps), kst = dm.kstages(phase);
             for (int c = 0; c < nch; ++c) {
-              if (!dm.owns(phase, c)) continue;
               const bool feat = phase == 3 && c == 0;
-              const uint32_t ncols = feat ? (uint32_t)O : 256u;
               const uint32_t idesc = feat ? idesc_feat : idesc_wide;
-              const uint32_t b_lbo = ncols * 16u;
+              const uint32_t b_lbo = feat ? 64u * 16u : 128u * 16u;          // rows of THIS CTA's half x 16 B
               const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
-              mbar_wait(&sh.tmem_empty[buf], (use & 1u) ^ 1u);
-              tc_fence_after();
-              db_trace(p, 100 + phase * 10 + c);
+              if (rank == 0) {
+                mbar_wait(&sh.tmem_empty[buf], (use & 1u) ^ 1u);
+                if (use > 0) mbar_wait(&sh.peer_tmem_empty[buf], (use & 1u) ^ 1u);   // completion #(use-1): the peer drained it too
+                tc_fence_after();
+                db_trace(p, 100 + phase * 10 + c);
+              }
               const uint32_t d_tmem = tmem + buf * 256u;
               for (int ks = 0; ks < kst; ++ks) {
                 mbar_wait(&sh.full[stage], sphase);
-                tc_fence_after();
-                if (ks == 0) db_trace(p, 200 + phase * 10 + c);
-                const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes);
-                const uint32_t b_addr = a_addr + kABytes;
+                if (rank == 1) {
+                  mbar_arrive_remote(&sh.peer_full[stage], 0);               // tell the leader our half has landed
+                } else {
+                  mbar_wait(&sh.peer_full[stage], sphase);
+                  tc_fence_after();
+                  if (ks == 0) db_trace(p, 200 + phase * 10 + c);
+                  const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes);
+                  const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t ad = smem_desc(a_addr + (uint32_t)k * 4096u, 2048u, 128u);
-                  const uint64_t bd = smem_desc(b_addr + (uint32_t)k * 2u * b_lbo, b_lbo, 128u);
-                  mma_bf16_ss(d_tmem, ad, bd, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+                  for (int k = 0; k < 4; ++k) {
+                    const uint64_t ad = smem_desc(a_addr + (uint32_t)k * 4096u, 2048u, 128u);
+                    const uint64_t bd = smem_desc(b_addr + (uint32_t)k * 2u * b_lbo, b_lbo, 128u);
+                    mma2_bf16_ss(d_tmem, ad, bd, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+                  }
+                  mma2_commit(&sh.empty[stage]);                             // frees the stage in BOTH CTAs
                 }
-                mma_commit(&sh.empty[stage]);
                 if (++stage == kDbStages) { stage = 0; sphase ^= 1u; }
               }
-              mma_commit(&sh.tmem_full[buf]);
-              db_trace(p, 300 + phase * 10 + c);
+              if (rank == 0) {
+                mma2_commit(&sh.tmem_full[buf]);                             // accumulator ready in BOTH CTAs
+                db_trace(p, 300 + phase * 10 + c);
+              }
+              ++chunk_ctr;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ================================================================ peer only: "accumulator drained" relay
+    if (rank == 1 && elect_one()) {
+      uint32_t chunk_ctr = 0;
+      for (int tk = 0, st; (st = DB_TILE(tk)) >= 0; ++tk) {
+        const int steps = min(max(p.dur[p.order[(size_t)st * 256]], 0), FCL_MAX_DURATION);
+        for (int m = 0; m < steps; ++m) {
+          for (int phase = 0; phase < 4; ++phase) {
+            const int nch = dm.nchunks(phase, m + 1 == steps);
+            for (int c = 0; c < nch; ++c) {
+              const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
+              if (use > 0) {
+                mbar_wait(&sh.tmem_empty[buf], (use & 1u) ^ 1u);             // our epilogue finished use-1 of this buffer
+                mbar_arrive_remote(&sh.peer_tmem_empty[buf], 0);
+              }
               ++chunk_ctr;
             }
           }
@@ -295,17 +356,18 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
     const uint32_t drop_thr = dropout_threshold16(p.dropout_p);
     const float drop_scale = use_drop ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
 
-    for (int tk = 0, tile; (tile = DB_TILE(tk)) >= 0; ++tk) {
+    for (int tk = 0, st; (st = DB_TILE(tk)) >= 0; ++tk) {
+      const int tile = 2 * st + (int)rank;
       const int sidx = tile * 128 + r;
       int row = -1, d = 0, foff = 0, utt = 0, ph = 0;
-      if (sidx < p.n_rows) {
+      if (tile < p.n_tiles && sidx < p.n_rows) {
         row = p.order[sidx];
         d = min(max(p.dur[row], 0), FCL_MAX_DURATION);
         foff = p.frame_off[row];
         utt = p.row_utt[row];
         ph = p.row_phone[row];
       }
-      const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
+      const int steps = min(max(p.dur[p.order[(size_t)st * 256]], 0), FCL_MAX_DURATION);
       if (steps == 0) continue;
       const int zset = dm.C > 1 ? (tk & 1) : 0;      // one set is enough without a group (keeps the scratch L2-resident)
       // ---- tile init: x1 of step 0 (the first input frame is zero: prenet.0 sees only its bias) and zero z images
@@ -474,99 +536,48 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  cluster_sync_all();                                   // the leader's MMAs read the peer's shared memory: leave together
+  if (warp == 2) tmem_dealloc2(tmem, 512);
 }
+
+}  // namespace pair
+
 
 }  // namespace fcl
 
-namespace fcl {
-// Longest-processing-time assignment: tiles are duration-descending; each goes to the currently least-loaded slot
-// (ties -> lowest slot). One warp: lane l owns slots l, l+32, ...; the argmin over all slots is ONE redux.sync on the
-// key (load << 8 | slot), so an iteration costs tens of cycles (~15 us for 650 tiles). (Assigning whole rounds of
-// n_slots tiles at once is faster still but its makespan was 10 % worse on the LJSpeech-shaped batch.)
-__global__ void __launch_bounds__(256, 1)
-decoder_schedule_kernel(FclDecoderScheduleParams p) {
-  extern __shared__ int s_steps[];                    // steps of every tile, loaded in parallel first
-  for (int t = threadIdx.x; t < p.n_tiles; t += blockDim.x)
-    s_steps[t] = min(max(p.dur[p.order[(size_t)t * p.unit_rows]], 0), FCL_MAX_DURATION);
-  __syncthreads();
-  if (threadIdx.x >= 32) return;
-  constexpr int kPerLane = 8;                         // up to 256 slots
-  const int lane = threadIdx.x;
-  unsigned key[kPerLane];                             // (load << 8) | slot ; unused slots = max
-  int cnt[kPerLane];
-#pragma unroll
-  for (int i = 0; i < kPerLane; ++i) { key[i] = (lane + 32 * i) < p.n_slots ? (unsigned)(lane + 32 * i) : 0xFFFFFFFFu; cnt[i] = 0; }
-  unsigned lmin = key[0];
-#pragma unroll
-  for (int i = 1; i < kPerLane; ++i) lmin = min(lmin, key[i]);
-  for (int t = 0; t < p.n_tiles; ++t) {
-    const unsigned best = __reduce_min_sync(0xffffffffu, lmin);
-    const int bslot = (int)(best & 0xFFu);
-    if ((bslot & 31) == lane) {
-      unsigned nm = 0xFFFFFFFFu;
-#pragma unroll
-      for (int i = 0; i < kPerLane; ++i) {
-        if (bslot == lane + 32 * i) {
-          key[i] += (unsigned)(s_steps[t] + 1) << 8;
-          p.tile_slot[t] = bslot;
-          p.tile_rank[t] = cnt[i]++;
-        }
-        nm = min(nm, key[i]);
-      }
-      lmin = nm;
-    }
-  }
-}
-}  // namespace fcl
-
-extern "C" int fcl_decoder_schedule(const FclDecoderScheduleParams* p, void* stream) {
+extern "C" int fcl_decoder_bf16_pair(const FclDecoderBf16Params* p, void* stream) {
   using namespace fcl;
-  FCL_REQUIRE(p && p->order && p->dur && p->tile_slot && p->tile_rank, "null pointer");
-  FCL_REQUIRE(p->unit_rows == 128 || p->unit_rows == 256, "unit_rows must be 128 or 256");
-  FCL_REQUIRE(p->n_rows > 0 && p->n_tiles == (p->n_rows + p->unit_rows - 1) / p->unit_rows && p->n_slots >= 1 &&
-                  p->n_slots <= 256, "bad sizes");
-  FCL_REQUIRE(p->n_tiles <= 12000, "too many tiles for the single-CTA scheduler");
-  decoder_schedule_kernel<<<1, 256, (size_t)p->n_tiles * sizeof(int), as_stream(stream)>>>(*p);
-  return check_launch("fcl_decoder_schedule");
-}
-
-extern "C" int fcl_decoder_bf16_workspace(int32_t prenet_units, int32_t dunits, int64_t* priv_bytes_per_cta,
-                                          int64_t* shared_bytes_per_group, int64_t* c_floats_per_cta) {
-  if (!priv_bytes_per_cta || !shared_bytes_per_group || !c_floats_per_cta) return FCL_EINVAL;
-  *priv_bytes_per_cta = (int64_t)fcl::db_priv_bytes(prenet_units);
-  *shared_bytes_per_group = (int64_t)fcl::db_shared_bytes(dunits);
-  *c_floats_per_cta = (int64_t)2 * dunits * 128;
-  return FCL_OK;
-}
-
-extern "C" int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream) {
-  using namespace fcl;
+  using namespace fcl::pair;
   FCL_REQUIRE(p && p->order && p->dur && p->frame_off && p->row_utt && p->row_phone && p->hn_img &&
                   p->w_stream && p->bp0 && p->bp1 && p->wpos && p->b0 && p->b1 && p->act_priv && p->act_shared &&
-                  p->c_ws && p->before && p->tile_slot && p->tile_rank && p->group_sync,
+                  p->c_ws && p->before && p->tile_slot && p->tile_rank,
               "null pointer");
-  FCL_REQUIRE(p->group >= 1 && p->group <= 16 && p->n_slots % p->group == 0, "group must divide n_slots (1..16)");
-  FCL_REQUIRE((long long)p->n_tiles <= (long long)kDbMaxTilesPerCta * (p->n_slots / p->group), "too many tiles for the per-CTA tile list");
   FCL_REQUIRE(p->eunits % 64 == 0 && p->eunits >= 64, "eunits must be a multiple of 64");
   FCL_REQUIRE(p->n_rows > 0 && p->n_tiles == (p->n_rows + 127) / 128, "n_tiles must be ceil(n_rows / 128)");
   FCL_REQUIRE(p->prenet_units == 256, "prenet_units must be 256 (one 256-column chunk)");
   FCL_REQUIRE(p->dunits % 64 == 0 && p->dunits >= 64, "dunits must be a multiple of 64");
   FCL_REQUIRE(p->odim % 16 == 0 && p->odim <= 128, "odim must be a multiple of 16, <= 128");
-  FCL_REQUIRE(p->n_slots >= 1, "n_slots must be >= 1");
+  FCL_REQUIRE(p->n_slots >= 2 && p->n_slots % 2 == 0, "n_slots must be even (CTA pairs)");
   FCL_REQUIRE(p->zoneout >= 0.f && p->zoneout < 1.f && p->dropout_p >= 0.f && p->dropout_p < 1.f, "bad rates");
+  FCL_REQUIRE((long long)((p->n_tiles + 1) / 2) <= (long long)kDbMaxTilesPerCta * (p->n_slots / 2), "too many tiles");
   const size_t smem = (size_t)kDbStages * kStageBytes;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(decoder_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("fcl_decoder_bf16: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
+    cudaError_t e = cudaFuncSetAttribute(decoder_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("fcl_decoder_bf16_pair: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
     attr_done = true;
   }
-  // n_slots CTAs = n_slots / group groups; the spin barriers of group mode need every CTA resident: one CTA per SM,
-  // n_slots <= SM count (checked by the caller against fcl_sm_count()).
-  cudaError_t e = cudaMemsetAsync(p->group_sync, 0, sizeof(int32_t) * 2 * (size_t)(p->n_slots / p->group), as_stream(stream));
-  if (e != cudaSuccess) { set_error("fcl_decoder_bf16: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
-  decoder_bf16_kernel<<<p->n_slots, kDbThreads, smem, as_stream(stream)>>>(*p);
-  return check_launch("fcl_decoder_bf16");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)p->n_slots);
+  cfg.blockDim = dim3(kDbThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, decoder_bf16_pair_kernel, *p);
+  if (e != cudaSuccess) { set_error("fcl_decoder_bf16_pair: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
+  return check_launch("fcl_decoder_bf16_pair");
 }

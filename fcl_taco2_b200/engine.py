@@ -61,6 +61,7 @@ class Engine:
                        if bf16_gemms is None or k in bf16_gemms}
             self.bf16_decoder = bf16_decoder
             self.dec_stream = _pack.pack_decoder_stream(packed, hp).to(self.device)
+            self.dec_stream_pair = _pack.pack_decoder_stream(packed, hp, pair=True).to(self.device)
             self.blstm_whh_bf16 = None
             if "blstm_wih" in self.wb and (4 * (hp.eunits // 2)) % 256 == 0:
                 self.blstm_whh_bf16 = _pack.pack_bilstm_whh_bf16(packed).to(self.device)
@@ -75,6 +76,7 @@ class Engine:
         self._arena, self._arena_views, self._arena_seq, self._in_pass = [], [], 0, False
         self._stream_handle = None
         self.force_group = 0             # decoder group size override (tests); 0 = choose from the tile count
+        self.use_pair = False            # cta_group::2 decoder (pairs of CTAs) when there are enough tiles
         self.use_encoder_stack = False   # measured: with 256 channels only a 2-stage weight ring fits beside the images
         self.stage_events = None      # when a list: (stage, start_event, stop_event) appended per stage (bench.py)
 
@@ -288,11 +290,20 @@ class Engine:
             if -(-gate_chunks // g) < -(-gate_chunks // group):      # fewer chunks per CTA
                 group = g
         group = self.force_group or group
+        if self.use_pair and group == 1 and n_tiles >= 2:
+            # cta_group::2: pairs of CTAs walk super-tiles of 256 rows
+            n_super = (n_tiles + 1) // 2
+            n_pairs = min(self.n_slots // 2, n_super)
+            sched = self._buf((2, n_super), torch.int32)
+            self._call("fcl_decoder_schedule", _lib.DecoderScheduleParams(n_rows=P, n_tiles=n_super, n_slots=n_pairs,
+                                                                          unit_rows=256, order=dptr(order), dur=dptr(dur),
+                                                                          tile_slot=dptr(sched[0]), tile_rank=dptr(sched[1])))
+            return -1, n_pairs, 2 * n_pairs, sched          # group -1 marks pair mode
         n_groups = min(self.n_slots // group, n_tiles)
         n_slots = n_groups * group
         sched = self._buf((2, n_tiles), torch.int32)
         self._call("fcl_decoder_schedule", _lib.DecoderScheduleParams(n_rows=P, n_tiles=n_tiles, n_slots=n_groups,
-                                                                      order=dptr(order), dur=dptr(dur),
+                                                                      unit_rows=128, order=dptr(order), dur=dptr(dur),
                                                                       tile_slot=dptr(sched[0]), tile_rank=dptr(sched[1])))
         return group, n_groups, n_slots, sched
 
@@ -313,9 +324,9 @@ class Engine:
         p = _lib.DecoderBf16Params(n_rows=P, n_tiles=n_tiles, n_slots=n_slots, eunits=E, dunits=H,
                                    prenet_units=hp.prenet_units, odim=O, order=dptr(order), dur=dptr(dur),
                                    frame_off=dptr(frame_off), row_utt=dptr(row_utt), row_phone=dptr(row_phone),
-                                   hn_img=dptr(hn_img), w_stream=dptr(self.dec_stream),
+                                   hn_img=dptr(hn_img), w_stream=dptr(self.dec_stream_pair if group < 0 else self.dec_stream),
                                    bp0=dptr(w["dec_bp0"]), bp1=dptr(w["dec_bp1"]), wpos=dptr(w["dec_wpos"]),
-                                   b0=dptr(w["dec_g0h_b"]), b1=dptr(w["dec_b1"]), group=group,
+                                   b0=dptr(w["dec_g0h_b"]), b1=dptr(w["dec_b1"]), group=max(group, 1),
                                    act_priv=dptr(self.dec_act_priv), act_shared=dptr(self.dec_act_shared),
                                    c_ws=dptr(self.dec_c_ws), group_sync=dptr(self.dec_group_sync), before=dptr(before),
                                    zoneout=zoneout,
@@ -323,7 +334,7 @@ class Engine:
                                    tile_rank=dptr(sched[1]), trace=dptr(trace),
                                    trace_cap=(trace.numel() - 2) // 2 if trace is not None else 0)
         with self.stage("decoder_loop"):
-            self._call("fcl_decoder_bf16", p)
+            self._call("fcl_decoder_bf16_pair" if group < 0 else "fcl_decoder_bf16", p)
         return before
 
     def conv_stack(self, keys, acts, x, ld_in, rows, seg_off, n_segs, max_len_sum_tiles, taps=5, gather=None,

@@ -141,7 +141,13 @@ def pack_bf16(packed_fp32: dict) -> dict:
     return out
 
 
-def pack_decoder_stream(packed_fp32: dict, hp) -> torch.Tensor:
+def _split_halves(blocks: torch.Tensor, n: int) -> torch.Tensor:
+    """bf16 stage blocks [..][8][n][8] -> [..][2 halves][8][n/2][8]: each CTA of a pair loads its half of the columns."""
+    b = blocks.reshape(-1, 8, 2, n // 2, 8).permute(0, 2, 1, 3, 4).contiguous()
+    return b.reshape(-1)
+
+
+def pack_decoder_stream(packed_fp32: dict, hp, pair: bool = False) -> torch.Tensor:
     """bf16 weight stream of the tensor-core decoder, in the order the kernel consumes it each step
     (csrc/decoder_bf16.cu):
         P1  prenet.1                                   rows [x1]            256 cols
@@ -160,6 +166,15 @@ def pack_decoder_stream(packed_fp32: dict, hp) -> torch.Tensor:
     l1 = torch.cat([w1[H:], w1[:H]], dim=0)          # [z1 ; z0']
     feat = torch.cat([packed_fp32["dec_y0h_w"][0], packed_fp32["dec_wf"]], dim=0)      # (E + H, O) rows [h ; z1']
     pc = (feat.double() @ packed_fp32["dec_wp0"].double()).float()                      # (E + H, U)
+    if pair:
+        # cta_group::2 kernel: every stage block is split along N into the two CTAs' halves; feat_out's odim columns are
+        # zero-padded to 128 so that both halves are whole core-matrix rows
+        featp = torch.zeros(feat.shape[0], 128)
+        featp[:, :O] = feat
+        wide = [packed_fp32["dec_wp1"], l0, l1, pc]
+        pk = [_split_halves(pack_conv_bf16(w.unsqueeze(0), 256, 64)[0], 256) for w in wide]
+        pf = _split_halves(pack_conv_bf16(featp.unsqueeze(0), 128, 64)[0], 128)
+        return torch.cat([pk[0], pk[1], pk[2], pf, pk[3]]).contiguous()
     parts = [
         pack_conv_bf16(packed_fp32["dec_wp1"].unsqueeze(0), 256, 64)[0],
         pack_conv_bf16(l0.unsqueeze(0), 256, 64)[0],

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 13
+#define FCL_ABI_VERSION 14
 
 enum {
   FCL_OK = 0,
@@ -348,7 +348,8 @@ typedef struct {
 /* Longest-processing-time assignment of the duration-sorted tiles to the persistent CTAs (tile cost = its
  * step count + 1): every CTA ends at about the same time. One warp, ~20 us. */
 typedef struct {
-  int32_t n_rows, n_tiles, n_slots;
+  int32_t n_rows, n_tiles, n_slots;   /* n_tiles = number of scheduled units = ceil(n_rows / unit_rows)  */
+  int32_t unit_rows;         /* rows per scheduled unit: 128 (a tile) or 256 (a super-tile of a CTA pair) */
   const int32_t* order;      /* (P) duration-descending row order */
   const int32_t* dur;        /* (P) */
   int32_t* tile_slot;        /* out (n_tiles) */
@@ -358,6 +359,12 @@ int fcl_decoder_schedule(const FclDecoderScheduleParams* p, void* stream);
 int fcl_decoder_bf16_workspace(int32_t prenet_units, int32_t dunits, int64_t* priv_bytes_per_cta,
                                int64_t* shared_bytes_per_group, int64_t* c_floats_per_cta);
 int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream);
+/* cta_group::2 variant: n_slots CTAs = n_slots/2 pairs (2-CTA clusters); each pair walks SUPER-tiles (tiles 2j, 2j+1)
+ * with one M=256 MMA stream and every weight stage split between the two SMs. Same parameters, except:
+ * `group` is ignored, tile_slot/tile_rank are indexed by super-tile (fcl_decoder_schedule with unit_rows = 256,
+ * n_slots = number of pairs), act_shared holds n_slots * shared_bytes_per_group, and w_stream uses the pair packing
+ * (pack.py: pack_decoder_stream(pair=True): each stage block = [half 0][half 1], feat_out columns padded to 128). */
+int fcl_decoder_bf16_pair(const FclDecoderBf16Params* p, void* stream);
 
 #ifdef __cplusplus
 }

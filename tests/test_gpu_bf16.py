@@ -214,3 +214,24 @@ def test_decoder_group_mode_bit_identical(bf16_engines, kind, groups):
     torch.cuda.synchronize()
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
+
+
+@pytest.mark.parametrize("kind,n_utts", [("S", 9), ("S", 12), ("T", 6)])
+def test_decoder_pair_mode_bit_identical(bf16_engines, kind, n_utts):
+    """cta_group::2 decoder (a CTA pair shares every weight stage, M = 256 MMAs) vs the single-CTA kernel:
+    same arithmetic per row, so identical bits; odd and even tile counts, a partial last tile."""
+    eng, sd, hp = bf16_engines(kind)
+    xs, ds = synth.synth_batch(n_utts, 3, fixed_len=47)          # 423 rows -> 4 tiles, 564 -> 5 tiles, 282 -> 3 tiles
+    pl = planmod.make_plan(xs, ds)
+    d, _ = eng.upload(pl)
+    hn = torch.randn(pl.n_rows, hp.eunits, generator=torch.Generator().manual_seed(7)).cuda()
+    frame_off, ufo, order, totals = eng.len_reg_scan(d["dur"], d["utt_off"], pl.n_utts)
+    F_ = int(pl.dur.sum())
+    eng.force_group, eng.use_pair = 1, False
+    ref = eng.decoder(hn, d["dur"], frame_off, order, d["row_utt"], d["row_phone"], F_, 0.1, 0.5, 5).clone()
+    eng.use_pair = True
+    got = eng.decoder(hn, d["dur"], frame_off, order, d["row_utt"], d["row_phone"], F_, 0.1, 0.5, 5).clone()
+    eng.force_group, eng.use_pair = 0, False
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()
+    assert torch.equal(got, ref), float((got - ref).abs().max())
