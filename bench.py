@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--latency-utts", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--pair", type=int, default=-1, help="cta_group::2 decoder: 1 on, 0 off, -1 engine default")
     ap.add_argument("--dropout", type=float, default=0.5, help="prenet dropout rate (reference default 0.5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -238,6 +239,8 @@ def main():
     m = M.from_preset(args.model, seed=args.seed, device=dev, precision=args.precision)
     m.set_prenet_dropout(rate=args.dropout, seed=1)
     eng = m.engine()
+    if args.pair >= 0:
+        eng.use_pair = bool(args.pair)
     xs, ds = workload(args, rank)
     pl = planmod.make_plan(xs, ds)
     n_frames = int(sum(int(d.sum()) for d in ds))

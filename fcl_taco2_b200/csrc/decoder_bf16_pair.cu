@@ -10,6 +10,13 @@
 //   * the peer tells the leader "my half of stage s has landed" and "my epilogue drained accumulator b" with remote
 //     mbarrier arrivals (mapa + mbarrier.arrive.shared::cluster) from two relay threads.
 // The pair walks SUPER-tiles (tiles 2j, 2j+1 of the duration-sorted order) for the step count of the longer one.
+//
+// STATUS (round 1): bit-identical to decoder_bf16.cu (tests/test_gpu_bf16.py::test_decoder_pair_mode_bit_identical) but
+// SLOWER on B200: S batch 1024 3.18 ms vs 2.41 ms, T batch 1024 35.1 vs 18.8 ms. The timeline (tools/decoder_trace.py
+// ... pair) shows ~1350 cycles per K stage against ~830 for the single-CTA kernel although every SM moves a third
+// fewer operand bytes; the epilogues got faster (4.5 k vs 7 k cycles per chunk). Suspected: with un-swizzled
+// (SWIZZLE_NONE) operand images the cross-SM half of B is fetched at DSMEM speed. It is therefore OFF by default
+// (Engine.use_pair); kept as the starting point for a swizzled-layout version in round 2.
 #include "common.cuh"
 #include "umma.cuh"
 

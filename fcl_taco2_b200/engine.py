@@ -76,7 +76,7 @@ class Engine:
         self._arena, self._arena_views, self._arena_seq, self._in_pass = [], [], 0, False
         self._stream_handle = None
         self.force_group = 0             # decoder group size override (tests); 0 = choose from the tile count
-        self.use_pair = False            # cta_group::2 decoder (pairs of CTAs) when there are enough tiles
+        self.use_pair = False            # cta_group::2 decoder (CTA pairs): correct but measured slower (see the .cu header)
         self.use_encoder_stack = False   # measured: with 256 channels only a 2-stage weight ring fits beside the images
         self.stage_events = None      # when a list: (stage, start_event, stop_event) appended per stage (bench.py)
 

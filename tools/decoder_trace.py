@@ -9,6 +9,7 @@ kind = sys.argv[1] if len(sys.argv) > 1 else "S"
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 m = M.from_preset(kind, seed=0, device="cuda:0", precision="bf16").set_prenet_dropout(rate=0.5, seed=1)
 eng = m.engine()
+eng.use_pair = len(sys.argv) > 3 and sys.argv[3] == "pair"
 xs, ds = synth.synth_batch(batch, 0)
 pl = planmod.make_plan(xs, ds)
 for _ in range(2):
