@@ -235,3 +235,27 @@ def test_decoder_pair_mode_bit_identical(bf16_engines, kind, n_utts):
     torch.cuda.synchronize()
     assert torch.isfinite(got).all()
     assert torch.equal(got, ref), float((got - ref).abs().max())
+
+
+def test_bf16_predicted_durations_and_forced_prosody():
+    """Predicted-duration path on the tensor-core engine: the pass syncs once for the frame count, output lengths
+    equal the sum of the durations the kernel itself predicted; forced f0/energy are honoured."""
+    from fcl_taco2_b200 import model as M
+    sd = dict(weights("S", 2))
+    sd["duration_predictor.linear.bias"] = torch.tensor([2.5])
+    m = M.from_preset("S", seed=None, device="cpu", precision="bf16")
+    m.load_state_dict(sd)
+    m = m.to("cuda:0").set_prenet_dropout(rate=0.5, seed=3)
+    xs, _ = synth.synth_batch(5, 44)
+    res = m.inference_batch(xs, return_result=True)
+    outs = res.per_utterance()
+    assert all(torch.isfinite(o).all() and o.shape[1] == 80 and o.shape[0] >= len(x) for o, x in zip(outs, xs))
+    assert sum(o.shape[0] for o in outs) == res.out.shape[0] == int(res.utt_frame_off[-1])
+    rs = np.random.RandomState(0)
+    f0 = [rs.randn(len(x)).astype(np.float32) for x in xs]
+    en = [rs.randn(len(x)).astype(np.float32) for x in xs]
+    ds = [np.full(len(x), 3) for x in xs]
+    a = m.inference_batch(xs, durs=ds, f0s=f0, energies=en)
+    b = m.inference_batch(xs, durs=ds)
+    assert all(o.shape == (3 * len(x), 80) for o, x in zip(a, xs))
+    assert not torch.equal(a[0], b[0])
