@@ -24,6 +24,15 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout. Libraries chat on fd 1 (NCCL prints its version banner there), so fd 1 is
+# pointed at stderr for the whole run and the JSON line is written to the saved, real stdout at the end.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 from fcl_taco2_b200 import synth, hparams            # noqa: E402
 
 # algorithmic work per unit (SURVEY.md 8(d) / BASELINE.md 3), MAC counts of the reference formulation
@@ -189,7 +198,7 @@ def run_reference(args, rank, world):
         "note": "the reference is Python and cannot travel to the GPU box: this is oracle/restate.py, the op-for-op "
                 "torch-CPU restatement validated against the reference in the build container",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(args, world):
@@ -361,7 +370,7 @@ def main():
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": thr, "kind": "port",
                                     "sample": f"first {n} utterances ({fr} frames) of the same workload, per-utterance "
                                               f"loop of oracle/restate.py (torch CPU fp32), {dt:.1f} s"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
