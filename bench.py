@@ -262,18 +262,27 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    counts = fdist.exchange_counts(n_frames, dev) if world > 1 else None   # forced durations: known before the pass
+    K_CHUNKS = 4
+    gather = None
+    if world > 1:   # forced durations: every rank's output chunk boundaries are known (and exchanged) before the pass
+        from fcl_taco2_b200.plan import output_chunks
+        per_utt = np.add.reduceat(pl.dur.astype(np.int64), pl.utt_off[:-1].astype(np.int64))
+        ch = output_chunks(np.concatenate([[0], np.cumsum(per_utt)]), K_CHUNKS)
+        bounds = [c[2] for c in ch] + [ch[-1][3]]
+        bounds += [bounds[-1]] * (K_CHUNKS + 1 - len(bounds))
+        gather = fdist.ChunkedGather(bounds, m.odim, dev)
 
     def one_step(timed):
         flush.fill_(rank + 1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         eng.stage_events = [] if timed else None
         e0.record()
-        res = eng.run_uploaded(pl, dinp, m.hp.zoneout_rate, args.dropout, 1)
-        gathered = None
         if world > 1:
-            with eng.stage("gather"):
-                gathered = fdist.gather_mels(res.out, counts=counts)
+            res = eng.run_uploaded(pl, dinp, m.hp.zoneout_rate, args.dropout, 1, out_chunks=K_CHUNKS, chunk_cb=gather.on_chunk)
+            with eng.stage("gather_tail"):
+                gather.finish()            # transfers were started chunk by chunk during the postnet
+        else:
+            res = eng.run_uploaded(pl, dinp, m.hp.zoneout_rate, args.dropout, 1)
         e1.record()
         return e0, e1, None, eng.stage_events, None    # results are dropped: holding K outputs alive would force a
                                                        # fresh cudaMalloc of the output buffer inside every timed step

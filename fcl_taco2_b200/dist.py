@@ -61,3 +61,47 @@ def scatter_results(shards, per_rank_outputs, n_total):
         for i, o in zip(idxs, outs):
             res[i] = o
     return res
+
+
+class ChunkedGather:
+    """Final gather of the ragged mels to `dst`, overlapped with the tail of the pass: the postnet is launched per
+    group of utterances (Engine.run_uploaded(out_chunks=K, chunk_cb=gather.on_chunk)) and each finished group is sent
+    while the next one still computes. The frame ranges of every rank's groups are exchanged up front (K+1 integers per
+    rank; with forced durations they are known on the host before the pass). The root's NVLink ingress
+    ((N-1) x F x odim x 4 bytes) stays the floor; what is hidden is the postnet time."""
+
+    def __init__(self, bounds, odim, device, dst: int = 0, group=None, dtype=torch.float32):
+        """bounds: this rank's chunk frame boundaries [f_0=0, f_1, ..., f_K=F] (same K on every rank)."""
+        self.ws, self.rank, self.dst, self.group = dist.get_world_size(group), dist.get_rank(group), dst, group
+        mine = torch.tensor(list(bounds), dtype=torch.int64, device=device)
+        allb = [torch.empty_like(mine) for _ in range(self.ws)]
+        dist.all_gather(allb, mine, group=group)
+        self.bounds = [b.cpu().tolist() for b in allb]
+        self.reqs = []
+        self.bufs = None
+        if self.rank == dst:
+            self.bufs = [None if r == dst else torch.empty((self.bounds[r][-1], odim), dtype=dtype, device=device)
+                         for r in range(self.ws)]
+
+    def on_chunk(self, k, out, f_lo, f_hi):
+        """Called by the engine right after chunk k's kernels were enqueued on the current stream."""
+        if self.ws == 1:
+            return
+        if self.rank == self.dst:
+            self.bufs[self.dst] = out
+            ops = []
+            for r in range(self.ws):
+                lo, hi = self.bounds[r][k], self.bounds[r][k + 1]
+                if r != self.dst and hi > lo:
+                    ops.append(dist.P2POp(dist.irecv, self.bufs[r][lo:hi], r, self.group))
+        else:
+            ops = [dist.P2POp(dist.isend, out[f_lo:f_hi], self.dst, self.group)] if f_hi > f_lo else []
+        if ops:
+            self.reqs.extend(dist.batch_isend_irecv(ops))
+
+    def finish(self):
+        """Make the current stream wait for all transfers. -> per-rank tensors on dst, else None."""
+        for r in self.reqs:
+            r.wait()
+        self.reqs = []
+        return self.bufs

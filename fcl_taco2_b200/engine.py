@@ -19,7 +19,7 @@ import torch
 from . import _lib
 from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, dptr
 from .hparams import HParams
-from .plan import BatchPlan
+from .plan import output_chunks, BatchPlan
 
 
 _ELEM_SIZE = {torch.float32: 4, torch.int32: 4, torch.bfloat16: 2, torch.int64: 8, torch.uint8: 1}
@@ -338,7 +338,7 @@ class Engine:
         return before
 
     def conv_stack(self, keys, acts, x, ld_in, rows, seg_off, n_segs, max_len_sum_tiles, taps=5, gather=None,
-                   residual=None, wkeys=None, final=False):
+                   residual=None, wkeys=None, final=False, out=None):
         """Fused conv stack (fcl_conv_stack_bf16) over the layers `keys`; returns None when the stack does not
         fit on chip (caller falls back to layer-by-layer fcl_conv_gemm_bf16)."""
         L = len(keys)
@@ -366,18 +366,39 @@ class Engine:
                                                                      seg_off=dptr(seg_off), tiles=dptr(tiles),
                                                                      n_tiles=dptr(count)))
         cout_last = layers[L - 1].cout
-        out = torch.empty((rows, cout_last), dtype=torch.float32, device=dev) if final else \
-            self._buf((rows, cout_last), torch.float32)
+        if out is None:
+            out = torch.empty((rows, cout_last), dtype=torch.float32, device=dev) if final else \
+                self._buf((rows, cout_last), torch.float32)
         self._call("fcl_conv_stack_bf16", _lib.ConvStackParams(n_layers=L, taps=taps, layers=layers, in_=dptr(x), ld_in=ld_in,
                                                                in_channels=in_channels, b_stages=0, gather=dptr(gather), tiles=dptr(tiles), n_tiles_dev=dptr(count),
                                                                n_tiles=max_tiles, residual=dptr(residual), ldr=cout_last,
                                                                out=dptr(out), ldo=cout_last))
         return out
 
-    def postnet(self, before, fseg, n_frames):
+    def postnet(self, before, fseg, n_frames, chunks=None, chunk_cb=None):
+        """`chunks` = [(first utt, last utt + 1, first frame, last frame + 1), ...] (processing order): the fused stack
+        is launched per chunk and `chunk_cb(k, out, frame_lo, frame_hi)` is called right after chunk k is enqueued, so a
+        consumer (the multi-GPU gather, a D2H copy) can start on finished frames while later chunks still compute."""
         hp, w = self.hp, self.w
         O, C = hp.odim, hp.postnet_chans
-        if self.precision == "bf16" and len(fseg) > 3 and all(f"post_conv{l}" in self.wb for l in range(5)):
+        stack_ok = self.precision == "bf16" and len(fseg) > 3 and all(f"post_conv{l}" in self.wb for l in range(5))
+        if stack_ok and chunks and chunk_cb is not None:
+            utt_frame_off, n_utts = fseg[3]
+            final = torch.empty((n_frames, O), dtype=torch.float32, device=self.device)
+            ok = True
+            for k, (u0, u1, f0, f1) in enumerate(chunks):
+                r = self.conv_stack([f"post_conv{l}" for l in range(5)], [ACT_TANH] * 4 + [ACT_NONE], before, O, n_frames,
+                                    utt_frame_off[u0:], u1 - u0, lambda s, f0=f0, f1=f1, n=u1 - u0: (f1 - f0 + s - 1) // s + n,
+                                    residual=before, out=final,
+                                    wkeys=[f"post_stack{l}" if f"post_stack{l}" in self.wb else f"post_conv{l}"
+                                           for l in range(5)])
+                if r is None:
+                    ok = False
+                    break
+                chunk_cb(k, final, f0, f1)
+            if ok:
+                return final
+        if stack_ok:
             utt_frame_off, n_utts = fseg[3]
             out = self.conv_stack([f"post_conv{l}" for l in range(5)], [ACT_TANH] * 4 + [ACT_NONE], before, O, n_frames,
                                   utt_frame_off, n_utts, lambda s: (n_frames + s - 1) // s + n_utts, residual=before,
@@ -385,6 +406,9 @@ class Engine:
                                   wkeys=[f"post_stack{l}" if f"post_stack{l}" in self.wb else f"post_conv{l}"
                                          for l in range(5)])
             if out is not None:
+                if chunks and chunk_cb is not None:
+                    for k, (u0, u1, f0, f1) in enumerate(chunks):
+                        chunk_cb(k, out, f0, f1)
                 return out
         x = self.conv_gemm(before, w["post_conv0_w"], w["post_conv0_b"], n_frames, O, C, 5, ACT_TANH, seg=fseg,
                            key="post_conv0")
@@ -392,8 +416,12 @@ class Engine:
             x = self.conv_gemm(x, w[f"post_conv{l}_w"], w[f"post_conv{l}_b"], n_frames, C, C, 5, ACT_TANH, seg=fseg,
                                key=f"post_conv{l}")
         final = torch.empty((n_frames, O), dtype=torch.float32, device=self.device)     # returned to the caller
-        return self.conv_gemm(x, w["post_conv4_w"], w["post_conv4_b"], n_frames, C, O, 5, ACT_NONE, seg=fseg,
-                              residual=before, key="post_conv4", out=final)
+        out = self.conv_gemm(x, w["post_conv4_w"], w["post_conv4_b"], n_frames, C, O, 5, ACT_NONE, seg=fseg,
+                             residual=before, key="post_conv4", out=final)
+        if chunks and chunk_cb is not None:
+            for k, (u0, u1, f0, f1) in enumerate(chunks):          # not chunkable: hand everything over at the end
+                chunk_cb(k, out, f0, f1)
+        return out
 
     # ------------------------------------------------------------------ whole pass
     def upload(self, plan: BatchPlan):
@@ -455,16 +483,16 @@ class Engine:
 
     @torch.no_grad()
     def run_uploaded(self, plan: BatchPlan, d: dict, zoneout: float, dropout_p: float, dropout_seed: int,
-                     extras: bool = False, tile_rows=None, h2d: int = 0) -> BatchResult:
+                     extras: bool = False, tile_rows=None, h2d: int = 0, out_chunks: int = 0, chunk_cb=None) -> BatchResult:
         """The pass proper, inputs already resident on the device (`d` from `upload`)."""
         self._arena_seq, self._in_pass = 0, not extras     # extras (tests) keep intermediates: no recycling
         try:
-            return self._run_uploaded(plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d)
+            return self._run_uploaded(plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d, out_chunks, chunk_cb)
         finally:
             self._in_pass = False
             self._stream_handle = None
 
-    def _run_uploaded(self, plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d):
+    def _run_uploaded(self, plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d, out_chunks=0, chunk_cb=None):
         hp = self.hp
         B, P = plan.n_utts, plan.n_rows
         ex = {"h2d_bytes": h2d}
@@ -537,7 +565,8 @@ class Engine:
         before = self.decoder(hn, dur, frame_off, order, d["row_utt"], d["row_phone"], F, zoneout, dropout_p,
                               dropout_seed, tile_rows, schedule=sched)
         with self.stage("postnet"):
-            out = self.postnet(before, (fmap[2], fmap[3], ftiles, (utt_frame_off, B)), F)
+            chunks = output_chunks(ufo, out_chunks) if (out_chunks and chunk_cb is not None) else None
+            out = self.postnet(before, (fmap[2], fmap[3], ftiles, (utt_frame_off, B)), F, chunks, chunk_cb)
         if extras:
             ex.update(h=h, dlog=dlog, dur_pred=dur_pred, pitch=pitch, energy=energy, hn=hn, before=before,
                       frame_off=frame_off, order=order, frame_row=fmap[0], frame_step=fmap[1], position=pos,

@@ -90,3 +90,20 @@ def shard_utterances(costs, world_size: int):
         out[r].append(int(i))
         loads[r] += int(costs[i])
     return [sorted(o) for o in out]
+
+
+def output_chunks(utt_frame_off, k: int):
+    """Split the utterances (processing order) into <= k contiguous groups of about equal frame counts.
+    -> [(first utt, last utt + 1, first frame, last frame + 1), ...]; pure host arithmetic on the frame offsets."""
+    ufo = np.asarray(utt_frame_off, dtype=np.int64)
+    B, F = len(ufo) - 1, int(ufo[-1])
+    cuts = [0]
+    for i in range(1, k):
+        u = int(np.searchsorted(ufo, F * i // k, side="left"))
+        u = min(max(u, cuts[-1]), B)
+        if u > cuts[-1]:
+            cuts.append(u)
+    if cuts[-1] != B:
+        cuts.append(B)
+    return [(cuts[i], cuts[i + 1], int(ufo[cuts[i]]), int(ufo[cuts[i + 1]])) for i in range(len(cuts) - 1)
+            if ufo[cuts[i + 1]] > ufo[cuts[i]]]

@@ -64,3 +64,67 @@ def test_shard_and_gather_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert status == "ok" and sum(counts) == 23 and min(counts) >= 10
+
+
+def _chunk_worker(rank, world, port, lens, ret):
+    sys.path.insert(0, ROOT)
+    from fcl_taco2_b200 import dist as fdist
+    from fcl_taco2_b200.plan import output_chunks
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        K = 3
+        mine = fdist.my_shard(lens)
+        ufo = np.concatenate([[0], np.cumsum([int(lens[i]) for i in mine])])
+        chunks = output_chunks(ufo, K)
+        bounds = [c[2] for c in chunks] + [chunks[-1][3]]
+        bounds += [bounds[-1]] * (K + 1 - len(bounds))
+        g = fdist.ChunkedGather(bounds, 4, torch.device("cpu"))
+        out = torch.zeros((int(ufo[-1]), 4))
+        for k, (u0, u1, f0, f1) in enumerate(chunks):      # "compute" chunk k, then hand it to the gather
+            for u in range(u0, u1):
+                out[int(ufo[u]):int(ufo[u + 1])] = float(mine[u])
+            g.on_chunk(k, out, f0, f1)
+        bufs = g.finish()
+        if rank == 0:
+            ok = True
+            for r in range(world):
+                want = torch.cat([torch.full((int(lens[i]), 4), float(i)) for i in fdist.my_shard(lens, r, world)])
+                ok = ok and bufs[r].shape == want.shape and bool((bufs[r] == want).all())
+            ret.put("ok" if ok else "mismatch")
+        else:
+            assert bufs is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_chunked_gather_world2():
+    lens = np.random.RandomState(1).randint(5, 60, size=19)
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_chunk_worker, args=(r, 2, port, lens, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    status = ret.get(timeout=100)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert status == "ok"
+
+
+def test_output_chunks_cover_everything():
+    sys.path.insert(0, ROOT)
+    from fcl_taco2_b200.plan import output_chunks
+    rs = np.random.RandomState(2)
+    for B, K in ((1, 4), (3, 4), (50, 4), (50, 1), (7, 16)):
+        ufo = np.concatenate([[0], np.cumsum(rs.randint(1, 90, size=B))])
+        ch = output_chunks(ufo, K)
+        assert 1 <= len(ch) <= K and ch[0][0] == 0 and ch[0][2] == 0 and ch[-1][1] == B and ch[-1][3] == ufo[-1]
+        for a, b in zip(ch[:-1], ch[1:]):
+            assert a[1] == b[0] and a[3] == b[2]
+        for u0, u1, f0, f1 in ch:
+            assert f0 == ufo[u0] and f1 == ufo[u1] and f1 > f0

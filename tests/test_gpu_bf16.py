@@ -195,6 +195,29 @@ def test_fused_postnet_stack_matches_layer_by_layer(bf16_engines):
         assert err(fused[off[k]:off[k + 1]].cpu(), o)[0] < 8e-2
 
 
+def test_chunked_postnet_bit_identical(bf16_engines):
+    """Postnet launched per group of utterances (so that a gather / D2H of finished frames can overlap the rest):
+    tiles never cross utterances, so the result must equal the single-launch stack bit for bit."""
+    eng, sd, hp = bf16_engines("S")
+    lens = [300, 5, 1, 112, 113, 64, 700, 9, 250]
+    F_ = sum(lens)
+    before = torch.randn(F_, 80, generator=torch.Generator().manual_seed(2)).cuda()
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    lo = torch.from_numpy(np.repeat(off[:-1], lens)).cuda()
+    hi = torch.from_numpy(np.repeat(off[1:], lens)).cuda()
+    ufo = torch.from_numpy(off).cuda()
+    tiles = eng.conv_tiles(ufo, len(lens), sum((n + 127) // 128 for n in lens))
+    fseg = (lo, hi, tiles, (ufo, len(lens)))
+    whole = eng.postnet(before, fseg, F_)
+    seen = []
+    chunks = planmod.output_chunks(off, 4)
+    assert len(chunks) >= 3
+    chunked = eng.postnet(before, fseg, F_, chunks, lambda k, out, f0, f1: seen.append((k, f0, f1)))
+    torch.cuda.synchronize()
+    assert seen == [(k, c[2], c[3]) for k, c in enumerate(chunks)]
+    assert torch.equal(whole, chunked)
+
+
 @pytest.mark.parametrize("kind,groups", [("S", [2, 4]), ("T", [4, 16])])
 def test_decoder_group_mode_bit_identical(bf16_engines, kind, groups):
     """Group mode (several CTAs split one tile's gate columns, z exchanged through L2 with counter barriers) must
