@@ -244,6 +244,13 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
       uint32_t stage = 0, sphase = 0;
       uint32_t chunk_ctr = 0;                          // accumulator buffer = chunk_ctr & 1
       const uint32_t idesc_wide = idesc_bf16_f32(128u, 256u), idesc_feat = idesc_bf16_f32(128u, (uint32_t)O);
+      // Shared-memory descriptors, built incrementally: this thread shares its scheduler with four epilogue warps, so
+      // every instruction between two tcgen05.mma counts. low word = (address >> 4) | (LBO >> 4) << 16 (addresses are
+      // below 256 KB: no masking needed), high word = (SBO >> 4) | version 1 << 14, the same for every operand.
+      const uint32_t ring_lo = smem_u32(smem) >> 4;
+      constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+      constexpr uint32_t kALo = (2048u >> 4) << 16;   // A: LBO = 128 rows x 16 B
+      uint32_t s_lo = ring_lo;                         // descriptor address field of the current ring slot
       for (int tk = 0, tile; (tile = DB_TILE(tk)) >= 0; ++tk) {
         const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
         for (int m = 0; m < steps; ++m) {
@@ -255,6 +262,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
               const uint32_t ncols = feat ? (uint32_t)O : 256u;
               const uint32_t idesc = feat ? idesc_feat : idesc_wide;
               const uint32_t b_lbo = ncols * 16u;
+              const uint32_t b_lo = (kABytes >> 4) + ((b_lbo >> 4) << 16), b_kstep = (2u * b_lbo) >> 4;
               const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
               mbar_wait(&sh.tmem_empty[buf], (use & 1u) ^ 1u);
               tc_fence_after();
@@ -264,16 +272,15 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
                 mbar_wait(&sh.full[stage], sphase);
                 tc_fence_after();
                 if (ks == 0) db_trace(p, 200 + phase * 10 + c);
-                const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes);
-                const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  const uint64_t ad = smem_desc(a_addr + (uint32_t)k * 4096u, 2048u, 128u);
-                  const uint64_t bd = smem_desc(b_addr + (uint32_t)k * 2u * b_lbo, b_lbo, 128u);
+                  const uint64_t ad = ((uint64_t)kDescHi << 32) | (s_lo + (uint32_t)k * (4096u >> 4) + kALo);
+                  const uint64_t bd = ((uint64_t)kDescHi << 32) | (s_lo + b_lo + (uint32_t)k * b_kstep);
                   mma_bf16_ss(d_tmem, ad, bd, idesc, (ks > 0 || k > 0) ? 1u : 0u);
                 }
                 mma_commit(&sh.empty[stage]);
-                if (++stage == kDbStages) { stage = 0; sphase ^= 1u; }
+                s_lo += kStageBytes >> 4;
+                if (++stage == kDbStages) { stage = 0; sphase ^= 1u; s_lo = ring_lo; }
               }
               mma_commit(&sh.tmem_full[buf]);
               db_trace(p, 300 + phase * 10 + c);

@@ -8,15 +8,19 @@
 //   * the leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 for both; tcgen05.commit multicasts the
 //     "stage free" / "accumulator ready" arrivals to both CTAs' mbarriers;
 //   * the peer tells the leader "my half of stage s has landed" and "my epilogue drained accumulator b" with remote
-//     mbarrier arrivals (mapa + mbarrier.arrive.shared::cluster) from two relay threads.
+//     mbarrier arrivals (mapa + mbarrier.arrive.relaxed.cluster) from two relay threads. They must be .relaxed: with
+//     .release.cluster every arrival cost the relay thread ~1400 cycles and serialised the ring (tools/umma_rate.cu
+//     reproduces it in isolation: 1250-1500 vs 537 cycles per K=64 stage). Ordering does not need the release: the
+//     bytes were written by the bulk copy whose completion the relay thread observed (acquire) before it signals.
 // The pair walks SUPER-tiles (tiles 2j, 2j+1 of the duration-sorted order) for the step count of the longer one.
 //
-// STATUS (round 1): bit-identical to decoder_bf16.cu (tests/test_gpu_bf16.py::test_decoder_pair_mode_bit_identical) but
-// SLOWER on B200: S batch 1024 3.18 ms vs 2.41 ms, T batch 1024 35.1 vs 18.8 ms. The timeline (tools/decoder_trace.py
-// ... pair) shows ~1350 cycles per K stage against ~830 for the single-CTA kernel although every SM moves a third
-// fewer operand bytes; the epilogues got faster (4.5 k vs 7 k cycles per chunk). Suspected: with un-swizzled
-// (SWIZZLE_NONE) operand images the cross-SM half of B is fetched at DSMEM speed. It is therefore OFF by default
-// (Engine.use_pair); kept as the starting point for a swizzled-layout version in round 2.
+// STATUS (round 1): bit-identical to decoder_bf16.cu (tests/test_gpu_bf16.py::test_decoder_pair_mode_bit_identical) and
+// faster once every SM has a tile anyway: S batch 1024 2.13 ms vs 2.40 ms, T batch 1024 15.4 vs 18.8 ms (the MMA
+// stream runs at 500-570 cycles per K stage against ~800 for the single-CTA kernel, whose ring is limited by the
+// bulk-copy bytes in flight per SM). Engine.use_pair = None picks it when n_tiles >= SM count.
+// Tried and rejected (measured slower, both kernels): evaluating the dropout Philox stream ahead of the prenet
+// epilogues, either in the epilogue warps' waiting windows or in two extra warps through shared memory
+// (S batch 1024: 2.40 -> 2.64 ms single, 2.13 -> 2.48 ms pair).
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -80,7 +84,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
@@ -282,6 +286,11 @@ decoder_bf16_pair_kernel(FclDecoderBf16Params p) {
       uint32_t stage = 0, sphase = 0;
       uint32_t chunk_ctr = 0;                          // accumulator buffer = chunk_ctr & 1
       const uint32_t idesc_wide = idesc_bf16_f32(256u, 256u), idesc_feat = idesc_bf16_f32(256u, 128u);
+      // descriptors built incrementally (see decoder_bf16.cu): low word = (address >> 4) | (LBO >> 4) << 16
+      const uint32_t ring_lo = smem_u32(smem) >> 4;
+      constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+      constexpr uint32_t kALo = (2048u >> 4) << 16;
+      uint32_t s_lo = ring_lo;
       for (int tk = 0, st; (st = DB_TILE(tk)) >= 0; ++tk) {
         const int steps = min(max(p.dur[p.order[(size_t)st * 256]], 0), FCL_MAX_DURATION);
         for (int m = 0; m < steps; ++m) {
@@ -291,6 +300,7 @@ decoder_bf16_pair_kernel(FclDecoderBf16Params p) {
               const bool feat = phase == 3 && c == 0;
               const uint32_t idesc = feat ? idesc_feat : idesc_wide;
               const uint32_t b_lbo = feat ? 64u * 16u : 128u * 16u;          // rows of THIS CTA's half x 16 B
+              const uint32_t b_lo = (kABytes >> 4) + ((b_lbo >> 4) << 16), b_kstep = (2u * b_lbo) >> 4;
               const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
               if (rank == 0) {
                 mbar_wait(&sh.tmem_empty[buf], (use & 1u) ^ 1u);
@@ -307,17 +317,16 @@ decoder_bf16_pair_kernel(FclDecoderBf16Params p) {
                   mbar_wait(&sh.peer_full[stage], sphase);
                   tc_fence_after();
                   if (ks == 0) db_trace(p, 200 + phase * 10 + c);
-                  const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes);
-                  const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    const uint64_t ad = smem_desc(a_addr + (uint32_t)k * 4096u, 2048u, 128u);
-                    const uint64_t bd = smem_desc(b_addr + (uint32_t)k * 2u * b_lbo, b_lbo, 128u);
+                    const uint64_t ad = ((uint64_t)kDescHi << 32) | (s_lo + (uint32_t)k * (4096u >> 4) + kALo);
+                    const uint64_t bd = ((uint64_t)kDescHi << 32) | (s_lo + b_lo + (uint32_t)k * b_kstep);
                     mma2_bf16_ss(d_tmem, ad, bd, idesc, (ks > 0 || k > 0) ? 1u : 0u);
                   }
                   mma2_commit(&sh.empty[stage]);                             // frees the stage in BOTH CTAs
                 }
-                if (++stage == kDbStages) { stage = 0; sphase ^= 1u; }
+                s_lo += kStageBytes >> 4;
+                if (++stage == kDbStages) { stage = 0; sphase ^= 1u; s_lo = ring_lo; }
               }
               if (rank == 0) {
                 mma2_commit(&sh.tmem_full[buf]);                             // accumulator ready in BOTH CTAs

@@ -76,7 +76,7 @@ class Engine:
         self._arena, self._arena_views, self._arena_seq, self._in_pass = [], [], 0, False
         self._stream_handle = None
         self.force_group = 0             # decoder group size override (tests); 0 = choose from the tile count
-        self.use_pair = False            # cta_group::2 decoder (CTA pairs): correct but measured slower (see the .cu header)
+        self.use_pair = None             # cta_group::2 decoder (CTA pairs): None = when every SM has a tile anyway; True / False force it
         self.use_encoder_stack = False   # measured: with 256 channels only a 2-stage weight ring fits beside the images
         self.stage_events = None      # when a list: (stage, start_event, stop_event) appended per stage (bench.py)
 
@@ -290,7 +290,8 @@ class Engine:
             if -(-gate_chunks // g) < -(-gate_chunks // group):      # fewer chunks per CTA
                 group = g
         group = self.force_group or group
-        if self.use_pair and group == 1 and n_tiles >= 2:
+        use_pair = self.use_pair if self.use_pair is not None else n_tiles >= self.n_slots
+        if use_pair and group == 1 and n_tiles >= 2:
             # cta_group::2: pairs of CTAs walk super-tiles of 256 rows
             n_super = (n_tiles + 1) // 2
             n_pairs = min(self.n_slots // 2, n_super)

@@ -254,7 +254,7 @@ def test_decoder_pair_mode_bit_identical(bf16_engines, kind, n_utts):
     ref = eng.decoder(hn, d["dur"], frame_off, order, d["row_utt"], d["row_phone"], F_, 0.1, 0.5, 5).clone()
     eng.use_pair = True
     got = eng.decoder(hn, d["dur"], frame_off, order, d["row_utt"], d["row_phone"], F_, 0.1, 0.5, 5).clone()
-    eng.force_group, eng.use_pair = 0, False
+    eng.force_group, eng.use_pair = 0, None
     torch.cuda.synchronize()
     assert torch.isfinite(got).all()
     assert torch.equal(got, ref), float((got - ref).abs().max())

@@ -10,6 +10,7 @@ batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 m = M.from_preset(kind, seed=0, device="cuda:0", precision="bf16").set_prenet_dropout(rate=0.5, seed=1)
 eng = m.engine()
 eng.use_pair = len(sys.argv) > 3 and sys.argv[3] == "pair"
+NLINES = int(sys.argv[4]) if len(sys.argv) > 4 else 140
 xs, ds = synth.synth_batch(batch, 0)
 pl = planmod.make_plan(xs, ds)
 for _ in range(2):
@@ -23,8 +24,8 @@ rec = rec[np.argsort(rec[:, 1], kind="stable")]
 t0 = rec[0, 1]
 print("records", n)
 # first ~2 steps as a timeline
-names = {1: "mma:acc_free", 2: "mma:stage0_landed", 3: "mma:issued", 4: "epi:acc_ready", 5: "epi:done", 6: "prod:operand_ready"}
-for ev, clk in rec[:140]:
+names = {7: "epi:detail", 1: "mma:acc_free", 2: "mma:stage0_landed", 3: "mma:issued", 4: "epi:acc_ready", 5: "epi:done", 6: "prod:operand_ready"}
+for ev, clk in rec[:NLINES]:
     kind_, rest = ev // 100, ev % 100
     print(f"{clk - t0:9d}  {names[kind_]:20s} phase {rest // 10 if kind_ != 6 else rest} chunk {rest % 10 if kind_ != 6 else '-'}")
 # aggregate: per (phase, chunk): issue time (300-200), wait for stage0 (200-100), epilogue (500-400), and step length
