@@ -361,34 +361,24 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
         }
 
         // ---------------- L0, L1: zoneout LSTM cells; per chunk this thread owns 16 hidden units of its row.
-        // The old cell state (fp32) and old z (bf16) of chunk c+1 are requested before chunk c is computed, and
-        // those of chunk 0 before waiting for its accumulator: their L2 latency hides behind the MMAs.
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
           const uint8_t* zcur = layer == 0 ? z0cur : z1cur;
           uint8_t* znew = layer == 0 ? z0new : z1new;
           float* cl = cws + (size_t)layer * H * 128;
           const float* bias = layer == 0 ? p.b0 : p.b1;
-          float c_cur[16], c_nxt[16];
-          uint4 z_cur[2], z_nxt[2];
-          const int c_first = dm.cr % dm.C;                           // this CTA's chunks: c_first, c_first + C, ...
-          if (c_first < dm.gate_chunks) {
-            const int u0 = c_first * 64 + cs * 16;
+          float c_cur[16];
+          uint4 z_cur[2];
+#pragma unroll 1
+          for (int c = dm.cr % dm.C; c < dm.gate_chunks; c += dm.C) {   // this CTA's chunks
+            const int u0 = c * 64 + cs * 16;                          // first of this thread's 16 hidden units
+            // old cell state / old z of this chunk: requested BEFORE waiting for the accumulator (their L2 latency hides
+            // behind the MMAs). No second register set for the next chunk: at 96 registers per thread it was spilled
+            // right after the loads, which made the "prefetch" a blocking load plus local-memory traffic.
 #pragma unroll
             for (int j = 0; j < 16; ++j) c_cur[j] = m == 0 ? 0.f : __ldcg(cl + (size_t)(u0 + j) * 128 + r);
             z_cur[0] = __ldcg(reinterpret_cast<const uint4*>(zcur + ((size_t)(u0 >> 3) * 128 + r) * 16));
             z_cur[1] = __ldcg(reinterpret_cast<const uint4*>(zcur + ((size_t)((u0 >> 3) + 1) * 128 + r) * 16));
-          }
-#pragma unroll 1
-          for (int c = c_first; c < dm.gate_chunks; c += dm.C) {
-            const int u0 = c * 64 + cs * 16;                          // first of this thread's 16 hidden units
-            if (c + dm.C < dm.gate_chunks) {
-              const int un = u0 + 64 * dm.C;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) c_nxt[j] = m == 0 ? 0.f : __ldcg(cl + (size_t)(un + j) * 128 + r);
-              z_nxt[0] = __ldcg(reinterpret_cast<const uint4*>(zcur + ((size_t)(un >> 3) * 128 + r) * 16));
-              z_nxt[1] = __ldcg(reinterpret_cast<const uint4*>(zcur + ((size_t)((un >> 3) + 1) * 128 + r) * 16));
-            }
             const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
             mbar_wait(&sh.tmem_full[buf], use & 1u);
             tc_fence_after();
@@ -428,9 +418,6 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
             *reinterpret_cast<uint4*>(znew + ((size_t)(u0 >> 3) * 128 + r) * 16) = make_uint4(zout[0], zout[1], zout[2], zout[3]);
             *reinterpret_cast<uint4*>(znew + ((size_t)((u0 >> 3) + 1) * 128 + r) * 16) = make_uint4(zout[4], zout[5], zout[6], zout[7]);
             if (tid == 128) db_trace(p, 500 + (1 + layer) * 10 + c);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) c_cur[j] = c_nxt[j];
-            z_cur[0] = z_nxt[0]; z_cur[1] = z_nxt[1];
           }
           fence_proxy_async_all();
           mbar_arrive(&sh.a_ready[2 + layer]);
