@@ -169,6 +169,13 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
   const uint32_t tmem = sh.tmem_base;
   const uint32_t b_bytes_wide = 256u * 64u * 2u, b_bytes_feat = (uint32_t)O * 64u * 2u;
 
+  // Register budget: the launch gives every thread 96 (65536 / 640, rounded down); the single-thread roles of warps
+  // 0-3 need far fewer, the epilogue (16 LSTM cells per thread in flight) spills at 96. Warps 0-3 release 32 each
+  // (4096 in total), the 512 epilogue threads take 8 more each (4096). Asking for 112 (exactly the 8192 that are free
+  // on paper) never returns: setmaxnreg.inc blocks until the pool can serve it, so keep a margin.
+  // (each setmaxnreg has to dominate the code it is meant for, hence the two-level role dispatch)
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == 0) {
     // ================================================================ producer
     if (elect_one()) {
@@ -291,7 +298,9 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ================================================================ epilogue (512 threads)
     const int q = warp & 3, cs = (warp - 4) >> 2;      // TMEM lane quarter, column quarter
     const int r = q * 32 + lane;                       // row within the tile == TMEM lane

@@ -208,6 +208,10 @@ decoder_bf16_pair_kernel(FclDecoderBf16Params p) {
   // per-CTA halves: 128 of the 256 gate/prenet columns, 64 of the feat_out columns (odim zero-padded to 128)
   const uint32_t b_bytes_wide = 128u * 64u * 2u, b_bytes_feat = 64u * 64u * 2u;
 
+  // Register budget (see decoder_bf16.cu): warps 0-3 give up 32 registers per thread, the epilogue threads get 16 more.
+  // Each setmaxnreg has to dominate the code it is meant for, hence the two-level role dispatch.
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == 0) {
     // ================================================================ producer
     if (elect_one()) {
@@ -361,7 +365,9 @@ decoder_bf16_pair_kernel(FclDecoderBf16Params p) {
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ================================================================ epilogue (512 threads)
     const int q = warp & 3, cs = (warp - 4) >> 2;      // TMEM lane quarter, column quarter
     const int r = q * 32 + lane;                       // row within the tile == TMEM lane
