@@ -405,7 +405,7 @@ decoder_bf16_pair_kernel(FclDecoderBf16Params p) {
           *reinterpret_cast<uint4*>(zsh + db_z_off(H, zset, 0) + ((size_t)kc * 128 + r) * 16) = z4;
           *reinterpret_cast<uint4*>(zsh + db_z_off(H, zset, 2) + ((size_t)kc * 128 + r) * 16) = z4;
         }
-        fence_proxy_async_all();
+        fence_proxy_async_global();
         mbar_arrive(&sh.a_ready[0]);
       }
 
@@ -432,7 +432,7 @@ decoder_bf16_pair_kernel(FclDecoderBf16Params p) {
           tc_fence_before();
           mbar_arrive(&sh.tmem_empty[buf]);
           ++chunk_ctr;
-          fence_proxy_async_all();
+          fence_proxy_async_global();
           mbar_arrive(&sh.a_ready[1]);
           if (tid == 128) db_trace(p, 500);
         }
@@ -496,7 +496,7 @@ decoder_bf16_pair_kernel(FclDecoderBf16Params p) {
             *reinterpret_cast<uint4*>(znew + ((size_t)((u0 >> 3) + 1) * 128 + r) * 16) = make_uint4(zout[4], zout[5], zout[6], zout[7]);
             if (tid == 128) db_trace(p, 500 + (1 + layer) * 10 + c);
           }
-          fence_proxy_async_all();
+          fence_proxy_async_global();
           mbar_arrive(&sh.a_ready[2 + layer]);
         }
 
@@ -512,7 +512,8 @@ decoder_bf16_pair_kernel(FclDecoderBf16Params p) {
             if (row >= 0 && m < d) {                                 // exhausted rows are masked (decoder_sa.py:625-629)
               float4* o = reinterpret_cast<float4*>(p.before + ((size_t)foff + m) * O + g * 16);
 #pragma unroll
-              for (int qd = 0; qd < 4; ++qd) o[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+              for (int qd = 0; qd < 4; ++qd)                          // streaming store: written once, read by the next kernel
+                __stcs(o + qd, make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]));
             }
           }
           tc_fence_before();
@@ -537,7 +538,7 @@ decoder_bf16_pair_kernel(FclDecoderBf16Params p) {
           tc_fence_before();
           mbar_arrive(&sh.tmem_empty[buf]);
           ++chunk_ctr;
-          fence_proxy_async_all();
+          fence_proxy_async_global();
           mbar_arrive(&sh.a_ready[0]);
           if (tid == 128) db_trace(p, 531);
         }

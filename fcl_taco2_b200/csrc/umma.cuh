@@ -49,6 +49,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // generic-proxy writes (st.shared / st.global) -> visible to the async proxy (tcgen05.mma operands, bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// global-memory writes only (activation images in the L2-resident scratch that bulk copies re-read)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // global -> shared bulk copy (1-D, contiguous); completes `bytes` on the mbarrier. 16-byte aligned, bytes % 16 == 0.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
