@@ -7,8 +7,9 @@
 
 A "step" = one pass of the whole hot path (encoder -> predictors -> length regulator -> decoder
 -> postnet) over one synthetic LJSpeech-shaped batch. `value` = frames of all ranks / device time
-(inputs resident in HBM); `e2e` = the same through model.inference_batch() with host buffers
-(H2D of the inputs and D2H of the mels inside the timed region).
+(inputs resident in HBM); `e2e` = the same through model.inference_stream() with host buffers
+(host planning, H2D of the inputs and D2H of the mels inside the timed region; the D2H of a batch overlaps
+the compute of the next one, as in the decode driver).
 """
 import argparse
 import json
@@ -314,22 +315,26 @@ def main():
             stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b)
     eng.stage_events = None
 
-    # ---- e2e through the public API: host ids/durations in, host mels out
-    host_out = torch.empty((n_frames, m.odim), dtype=torch.float32).pin_memory()
-    def e2e_step():
-        flush.fill_(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        res = m.inference_batch(xs, durs=ds, return_result=True)
-        host_out.copy_(res.out, non_blocking=True)
-        e1.record()
-        return e0, e1
-    for _ in range(2):
-        e2e_step()
+    # ---- e2e through the public API: host ids/durations in, host mels out. model.inference_stream() is the call a
+    # decode driver makes: every batch is planned on the host, uploaded, decoded, and its mels are copied to pinned host
+    # memory on a copy stream while the next batch computes. The timed region covers K whole batches, from the first
+    # upload to the arrival of the last batch's mels on the host (L2 flushed before every batch, inside the region).
+    def batches(k):
+        for _ in range(k):
+            yield {"xs": xs, "durs": ds}
+    flush_l2 = lambda: flush.fill_(1)
+    for _ in m.inference_stream(batches(6), before_batch=flush_l2):
+        pass
     barrier()
-    e2e_evs = [e2e_step() for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    got = 0
+    for outs in m.inference_stream(batches(args.steps), before_batch=flush_l2):      # the generator returns a batch only when it is on the host
+        got += len(outs)
+    e1.record()
     barrier()
-    e2e_ms = float(sum(a.elapsed_time(b) for a, b in e2e_evs))
+    assert got == args.steps * len(xs)
+    e2e_ms = float(e0.elapsed_time(e1))
 
     # ---- reduce over ranks: max time, sum frames
     t = torch.tensor([total_ms, e2e_ms, float(n_frames), float(n_rows), float(launches)], dtype=torch.float64, device=dev)

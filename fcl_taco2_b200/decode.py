@@ -11,7 +11,8 @@ Mirrors `tts.decode` / `tts_distill.decode` (reference tts.py:605-686, tts_disti
   * output: Kaldi "ark,scp" float32 matrices (tts.py:652,674: kaldiio.WriteHelper("ark,scp:{o}.ark,{o}.scp"))
   * per-utterance "inference speed = frames / sec", mean of ratios written to <exp_name>.txt (tts.py:669-684)
 
-New: utterances are decoded `--batch-size` at a time through `inference_batch` (the reference loops one by one).
+New: utterances are decoded `--batch-size` at a time through `inference_stream` (the reference loops one by one);
+the device->host copy and the ark write of a batch overlap the compute of the next one.
 
     python -m fcl_taco2_b200.decode --model exp/x/results/snapshot.ep.100 --json data/test_data.1.json \\
         --out decode/feats --ngpu 1 [--test-teacher true|false] [--batch-size 256] [--precision bf16]
@@ -150,15 +151,16 @@ def decode(args, teacher_args=None):
     utt_ids, xs = read_utts(args.json, getattr(args, "pad_eos", False))
     bs = max(1, int(getattr(args, "batch_size", 256)))
     speeds = []
+    starts = list(range(0, len(xs), bs))
+    batches = ({"xs": xs[b0:b0 + bs], "utt_ids": list(range(b0, min(b0 + bs, len(xs))))} for b0 in starts)
     with KaldiWriter(args.out) as writer:
-        for b0 in range(0, len(xs), bs):
-            chunk = xs[b0:b0 + bs]
-            t0 = time.time()
-            outs = model.inference_batch(chunk, utt_ids=list(range(b0, b0 + len(chunk))))
-            host = [o.cpu().numpy() for o in outs]      # includes the device synchronisation
+        t0 = time.time()
+        # batch i+1 computes while the mels of batch i travel to the host and are written to the ark
+        for b0, host in zip(starts, model.inference_stream(batches)):
             dt = time.time() - t0
+            t0 = time.time()
             frames = sum(h.shape[0] for h in host)
-            for utt, h in zip(utt_ids[b0:b0 + len(chunk)], host):
+            for utt, h in zip(utt_ids[b0:b0 + bs], host):
                 speeds.append(frames / dt)              # every utterance of a batch shares the batch's rate
                 logging.info("inference speed = %.1f frames / sec." % speeds[-1])
                 writer[utt] = h

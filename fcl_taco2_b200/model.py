@@ -190,10 +190,8 @@ class Tacotron2_sa(_TTSBase, torch.nn.Module):
     def forward(self, *a, **k):
         raise NotImplementedError("training forward()/losses are out of scope of the B200 inference path")
 
-    @torch.no_grad()
-    def inference_batch(self, xs, durs=None, f0s=None, energies=None, utt_ids=None, return_result=False):
-        """Batched form of `inference`: xs is a list of 1-D id sequences (LongTensor / ndarray / list).
-        -> list of (L_i, odim) float32 tensors on the model device, in the order given."""
+    def _plan(self, xs, durs=None, f0s=None, energies=None, utt_ids=None):
+        """Host side of a batch: validate, order longest-first, flatten (pure numpy, no CUDA calls)."""
         to_np = lambda v: v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
         xs = [to_np(x) for x in xs]
         if any(x.ndim != 1 for x in xs):
@@ -202,8 +200,98 @@ class Tacotron2_sa(_TTSBase, torch.nn.Module):
         pl = planmod.make_plan(xs, conv(durs), conv(f0s), conv(energies), utt_ids)
         if pl.ids.min() < 0 or pl.ids.max() >= self.idim:
             raise ValueError("phoneme id out of range")
+        return pl
+
+    @torch.no_grad()
+    def inference_batch(self, xs, durs=None, f0s=None, energies=None, utt_ids=None, return_result=False):
+        """Batched form of `inference`: xs is a list of 1-D id sequences (LongTensor / ndarray / list).
+        -> list of (L_i, odim) float32 tensors on the model device, in the order given."""
+        pl = self._plan(xs, durs, f0s, energies, utt_ids)
         res = self.engine().run(pl, self.hp.zoneout_rate, self._dropout_rate, self._seed_for_call())
         return res if return_result else res.per_utterance()
+
+    @torch.no_grad()
+    def inference_stream(self, batches, depth: int = 3, before_batch=None):
+        """Decode a sequence of batches with the device->host transfer of batch i overlapped with the compute of
+        batch i+1 (what a decode driver over a data set wants: the mels of a batch are ~180 MB, their PCIe transfer
+        takes about as long as half of the pass that produced them).
+
+        `batches`: iterable of `xs` lists or of dicts with the keyword arguments of `inference_batch`
+        (xs, durs, f0s, energies, utt_ids). Yields, in order, one list of (L_i, odim) float32 numpy arrays per batch
+        (caller's utterance order). The arrays are views of a pinned staging buffer that is reused `depth` batches
+        later: consume or copy them before advancing that far. `before_batch()` (optional) is called on the calling
+        thread right before a batch is enqueued (bench.py flushes L2 there)."""
+        dev = self.device
+        copy_stream = getattr(self, "_copy_stream", None)
+        if copy_stream is None:
+            copy_stream = self._copy_stream = torch.cuda.Stream(dev)
+            self._host_ring = []
+        pending = []                                                  # (result, host buffer, "copied" event)
+
+        def finish(item):
+            res, buf, ev = item
+            ev.synchronize()
+            host = buf[: res.out.shape[0]].numpy()
+            outs = [None] * len(res.perm)
+            for k, i in enumerate(res.perm):
+                outs[int(i)] = host[int(res.utt_frame_off[k]): int(res.utt_frame_off[k + 1])]
+            return outs
+
+        # host planning (flattening ~1000 small arrays takes milliseconds) runs one or two batches ahead in a thread;
+        # numpy and the ctypes launches release the GIL, so it overlaps the launches of the current batch
+        import queue
+        import threading
+        plans = queue.Queue(maxsize=2)
+
+        def planner():
+            try:
+                for b in batches:
+                    kw = b if isinstance(b, dict) else {"xs": b}
+                    plans.put(self._plan(**kw))
+                plans.put(None)
+            except BaseException as e:                                 # re-raised in the consumer
+                plans.put(e)
+
+        threading.Thread(target=planner, daemon=True).start()
+        engine = self.engine()
+        n = 0
+        while True:
+            pl = plans.get()
+            if pl is None:
+                break
+            if isinstance(pl, BaseException):
+                raise pl
+            if before_batch is not None:
+                before_batch()
+            res = engine.run(pl, self.hp.zoneout_rate, self._dropout_rate, self._seed_for_call())   # no host sync
+            slot = n % (depth + 1)                                    # depth in flight + the one the caller holds
+            n += 1
+            need = res.out.shape[0]
+            while len(self._host_ring) < depth + 1:
+                self._host_ring.append(None)
+            if n == 1:                                                # pinning is slow: size every slot on the first batch
+                for i in range(depth + 1):
+                    b_ = self._host_ring[i]
+                    if b_ is None or b_.shape[0] < need or b_.shape[1] != res.out.shape[1]:
+                        self._host_ring[i] = torch.empty((need * 5 // 4 + 1, res.out.shape[1]), dtype=torch.float32,
+                                                         pin_memory=True)
+            buf = self._host_ring[slot]
+            if buf.shape[0] < need or buf.shape[1] != res.out.shape[1]:
+                buf = self._host_ring[slot] = torch.empty((need * 5 // 4 + 1, res.out.shape[1]), dtype=torch.float32,
+                                                          pin_memory=True)
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(dev))
+            copied = torch.cuda.Event()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                buf[:need].copy_(res.out, non_blocking=True)
+                res.out.record_stream(copy_stream)
+                copied.record(copy_stream)
+            pending.append((res, buf, copied))
+            if len(pending) >= depth:
+                yield finish(pending.pop(0))
+        while pending:
+            yield finish(pending.pop(0))
 
     @torch.no_grad()
     def inference(self, x, inference_args=None, spemb=None, dur=None, f0=None, energy=None, utt_id=None,

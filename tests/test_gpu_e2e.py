@@ -119,3 +119,24 @@ def test_errors_are_loud(models):
         m.inference(torch.tensor([1, 2]), None, spemb=torch.zeros(4), dur=torch.tensor([1, 1]))
     with pytest.raises(NotImplementedError):
         m.forward()
+
+
+@pytest.mark.gpu
+def test_inference_stream_matches_inference_batch():
+    """The pipelined API (D2H of batch i overlapped with batch i+1) returns exactly what inference_batch returns,
+    batch by batch, also when the batches differ in size (the pinned staging ring is reused and regrown)."""
+    from fcl_taco2_b200 import model as M, synth
+    m = M.from_preset("S", seed=0, device="cuda:0", precision="bf16").set_prenet_dropout(rate=0.5, seed=3)
+    sets = [synth.synth_batch(n, seed) for n, seed in ((5, 1), (9, 2), (3, 3), (12, 4), (1, 5))]
+    want = []
+    for k, (xs, ds) in enumerate(sets):
+        outs = m.inference_batch(xs, durs=ds, utt_ids=list(range(100 * k, 100 * k + len(xs))))
+        want.append([o.cpu().numpy().copy() for o in outs])
+    batches = ({"xs": xs, "durs": ds, "utt_ids": list(range(100 * k, 100 * k + len(xs)))} for k, (xs, ds) in enumerate(sets))
+    n = 0
+    for k, outs in enumerate(m.inference_stream(batches)):
+        assert len(outs) == len(want[k])
+        for a, b in zip(outs, want[k]):
+            assert a.shape == b.shape and np.array_equal(a, b)
+        n += 1
+    assert n == len(sets)
