@@ -193,10 +193,10 @@ class Tacotron2_sa(_TTSBase, torch.nn.Module):
     def _plan(self, xs, durs=None, f0s=None, energies=None, utt_ids=None):
         """Host side of a batch: validate, order longest-first, flatten (pure numpy, no CUDA calls)."""
         to_np = lambda v: v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
-        xs = [to_np(x) for x in xs]
+        xs = [x if type(x) is np.ndarray else to_np(x) for x in xs]
         if any(x.ndim != 1 for x in xs):
             raise ValueError("each utterance must be a 1-D id sequence (encoder_sa.py:157)")
-        conv = lambda vs: None if vs is None else [to_np(v) for v in vs]
+        conv = lambda vs: None if vs is None else [v if type(v) is np.ndarray else to_np(v) for v in vs]
         pl = planmod.make_plan(xs, conv(durs), conv(f0s), conv(energies), utt_ids)
         if pl.ids.min() < 0 or pl.ids.max() >= self.idim:
             raise ValueError("phoneme id out of range")

@@ -29,24 +29,26 @@ class BatchPlan:
 
 def make_plan(xs, durs=None, f0s=None, energies=None, utt_ids=None) -> BatchPlan:
     """Vectorised: one concatenate per input stream + one gather into processing order (no per-utterance numpy
-    calls beyond the concatenation itself) -- this runs inside the end-to-end timed region."""
+    calls beyond the concatenation itself), int32 index arithmetic built with np.repeat -- this runs inside the
+    end-to-end timed region (about 1.5 ms for 1024 utterances / 80 k phonemes)."""
     B = len(xs)
     if B == 0:
         raise ValueError("empty batch")
-    lens = np.fromiter((len(x) for x in xs), dtype=np.int64, count=B)
+    lens = np.fromiter(map(len, xs), dtype=np.int64, count=B)
     if (lens <= 0).any():
         raise ValueError("zero-length utterance")
     perm = np.argsort(-lens, kind="stable")
-    utt_ids = np.arange(B, dtype=np.int64) if utt_ids is None else np.asarray(utt_ids, dtype=np.int64)
+    utt_ids = np.arange(B, dtype=np.int32) if utt_ids is None else np.asarray(utt_ids, dtype=np.int64).astype(np.int32)
     lens_p = lens[perm]
-    off = np.zeros(B + 1, dtype=np.int64)
-    off[1:] = np.cumsum(lens_p)
+    off = np.zeros(B + 1, dtype=np.int32)
+    np.cumsum(lens_p, out=off[1:])
     P = int(off[-1])
-    off_c = np.zeros(B + 1, dtype=np.int64)
-    off_c[1:] = np.cumsum(lens)                                   # caller-order offsets
-    rep = np.repeat(np.arange(B), lens_p)
-    within = np.arange(P) - off[:-1][rep]
-    gidx = off_c[:-1][perm][rep] + within                         # caller-order flat index of every processed row
+    off_c = np.zeros(B + 1, dtype=np.int32)
+    np.cumsum(lens, out=off_c[1:])                                # caller-order offsets
+    seg_lo = np.repeat(off[:-1], lens_p)
+    seg_hi = np.repeat(off[1:], lens_p)
+    within = np.arange(P, dtype=np.int32) - seg_lo
+    gidx = np.repeat(off_c[:-1][perm], lens_p) + within           # caller-order flat index of every processed row
 
     def cat(vals, dtype, what):
         if vals is None:
@@ -54,13 +56,15 @@ def make_plan(xs, durs=None, f0s=None, energies=None, utt_ids=None) -> BatchPlan
         if len(vals) != B:
             raise ValueError(f"{what} has {len(vals)} entries for {B} utterances")
         try:                                         # fast path: a list of 1-D arrays
-            vl = np.fromiter((v.shape[0] if v.ndim == 1 else -1 for v in vals), dtype=np.int64, count=B)
-            flat = np.concatenate(vals) if (vl >= 0).all() else None
-        except AttributeError:
+            flat = np.concatenate(vals)
+            vl = np.fromiter(map(len, vals), dtype=np.int64, count=B)
+            if flat.ndim != 1 or flat.shape[0] != int(vl.sum()):
+                flat = None
+        except (TypeError, ValueError):
             flat = None
-        if flat is None:                             # lists / (N,1) arrays
+        if flat is None:                             # lists / scalars / (N,1) arrays
             vals = [np.reshape(np.asarray(v), -1) for v in vals]
-            vl = np.fromiter((v.shape[0] for v in vals), dtype=np.int64, count=B)
+            vl = np.fromiter(map(len, vals), dtype=np.int64, count=B)
             flat = np.concatenate(vals)
         if (vl != lens).any():
             i = int(np.nonzero(vl != lens)[0][0])
@@ -69,12 +73,11 @@ def make_plan(xs, durs=None, f0s=None, energies=None, utt_ids=None) -> BatchPlan
 
     ids = cat(xs, np.int64, "xs")
     dur = cat(durs, np.int32, "durs")
-    if dur is not None and (dur < 0).any():
+    if dur is not None and dur.size and int(dur.min()) < 0:
         raise ValueError("negative duration")
     if (f0s is None) != (energies is None):
         raise ValueError("f0 and energy must be forced together (e2e_tts_tacotron2_sa.py:649-651)")
-    return BatchPlan(B, P, perm, ids, off.astype(np.int32), utt_ids[perm][rep].astype(np.int32),
-                     within.astype(np.int32), off[:-1][rep].astype(np.int32), off[1:][rep].astype(np.int32), dur,
+    return BatchPlan(B, P, perm, ids, off, np.repeat(utt_ids[perm], lens_p), within, seg_lo, seg_hi, dur,
                      cat(f0s, np.float32, "f0s"), cat(energies, np.float32, "energies"))
 
 
