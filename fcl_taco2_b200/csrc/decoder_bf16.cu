@@ -24,7 +24,8 @@
 // Warp roles (640 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4-19 = epilogue (TMEM lane quarter = warp % 4; column quarter = (warp - 4) / 4: 64 of a chunk's 256
 // columns). Gate columns are interleaved (unit*4 + {i,f,g,o}) so one thread owns whole LSTM cells; the old
-// cell state / old z of the NEXT chunk are requested before the current chunk is computed.
+// cell state / old z of a chunk are requested right before the thread waits for that chunk's accumulator.
+// setmaxnreg gives the epilogue threads 104 registers and leaves 64 to warps 0-3 (see the role dispatch).
 #include "common.cuh"
 #include "umma.cuh"
 

@@ -3,8 +3,8 @@
 // (see there for the algorithm and the reference lines); what changes is the operand path:
 //   * every weight stage is split along N: each CTA loads only ITS half (128 of 256 columns) and the tensor cores
 //     of both SMs consume both halves, so per SM a stage is 16 KB of A + 16 KB of B instead of 16 + 32 KB -- the
-//     single-CTA kernel is bound by shared-memory bandwidth in the MMA phases (every operand byte is written once
-//     by the bulk copy and read once by the MMA: 96 KB per 512-cycle stage against 128 B/clk);
+//     single-CTA kernel's ring is limited by the bulk-copy bytes an SM can keep in flight (a copy takes ~1080
+//     cycles whatever its size; 48 KB per 512-cycle stage does not fit, 32 KB does: tools/umma_rate.cu);
 //   * the leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 for both; tcgen05.commit multicasts the
 //     "stage free" / "accumulator ready" arrivals to both CTAs' mbarriers;
 //   * the peer tells the leader "my half of stage s has landed" and "my epilogue drained accumulator b" with remote
