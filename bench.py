@@ -377,6 +377,17 @@ def main():
                          "note": "algorithmic FLOPs = 2 x MAC per useful row-step (reference formulation, nothing hoisted) x frames"},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
         }
+        # the HBM-side view SURVEY 8(d) asks for next to the tensor roofline: algorithmic bytes / stage time, rank 0
+        sec = []
+        for name, key, nbytes in (("postnet (first input + last output only: 640 B/frame)", "postnet", 640.0 * n_frames),
+                                  ("length regulator scan + frame map (8 B/phoneme + 20 B/frame)", None,
+                                   8.0 * n_rows + 20.0 * n_frames)):
+            ms = (stage_ms.get(key, 0.0) if key else stage_ms.get("len_reg", 0.0) + stage_ms.get("frame_map", 0.0)) / args.steps
+            if ms > 0:
+                gbs = nbytes / (ms * 1e-3) / 1e9
+                sec.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                            "frac": gbs / pk["hbm"], "ms": ms})
+        line["roofline_secondary"] = sec
         if not args.no_extra:
             line["p50_utt_latency_ms"] = latency_p50(m, args, dev)
         if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only (torchrun pins OMP threads to 1)
