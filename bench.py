@@ -263,7 +263,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    K_CHUNKS = 4
+    # groups of utterances whose mels are sent while the next group's postnet runs; splitting the fused postnet costs
+    # ~0.2 ms, which only pays once the gather (bound by rank 0's ingress, (N-1) x 185 MB) is longer than that
+    K_CHUNKS = 1 if world <= 2 else 4
     gather = None
     if world > 1:   # forced durations: every rank's output chunk boundaries are known (and exchanged) before the pass
         from fcl_taco2_b200.plan import output_chunks
