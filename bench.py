@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--pair", type=int, default=-1, help="cta_group::2 decoder: 1 on, 0 off, -1 engine default")
+    ap.add_argument("--e2e-planner", type=int, default=0, help="inference_stream: plan batches in a helper thread (1) or inline (0)")
     ap.add_argument("--dropout", type=float, default=0.5, help="prenet dropout rate (reference default 0.5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -325,13 +326,13 @@ def main():
         for _ in range(k):
             yield {"xs": xs, "durs": ds}
     flush_l2 = lambda: flush.fill_(1)
-    for _ in m.inference_stream(batches(6), before_batch=flush_l2):
+    for _ in m.inference_stream(batches(6), before_batch=flush_l2, planner_thread=bool(args.e2e_planner)):
         pass
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     got = 0
-    for outs in m.inference_stream(batches(args.steps), before_batch=flush_l2):      # the generator returns a batch only when it is on the host
+    for outs in m.inference_stream(batches(args.steps), before_batch=flush_l2, planner_thread=bool(args.e2e_planner)):      # the generator returns a batch only when it is on the host
         got += len(outs)
     e1.record()
     barrier()

@@ -211,7 +211,7 @@ class Tacotron2_sa(_TTSBase, torch.nn.Module):
         return res if return_result else res.per_utterance()
 
     @torch.no_grad()
-    def inference_stream(self, batches, depth: int = 3, before_batch=None):
+    def inference_stream(self, batches, depth: int = 3, before_batch=None, planner_thread: bool = False):
         """Decode a sequence of batches with the device->host transfer of batch i overlapped with the compute of
         batch i+1 (what a decode driver over a data set wants: the mels of a batch are ~180 MB, their PCIe transfer
         takes about as long as half of the pass that produced them).
@@ -220,7 +220,8 @@ class Tacotron2_sa(_TTSBase, torch.nn.Module):
         (xs, durs, f0s, energies, utt_ids). Yields, in order, one list of (L_i, odim) float32 numpy arrays per batch
         (caller's utterance order). The arrays are views of a pinned staging buffer that is reused `depth` batches
         later: consume or copy them before advancing that far. `before_batch()` (optional) is called on the calling
-        thread right before a batch is enqueued (bench.py flushes L2 there)."""
+        thread right before a batch is enqueued (bench.py flushes L2 there). `planner_thread=True` moves the host-side
+        planning of the following batches to a helper thread."""
         dev = self.device
         copy_stream = getattr(self, "_copy_stream", None)
         if copy_stream is None:
@@ -232,13 +233,12 @@ class Tacotron2_sa(_TTSBase, torch.nn.Module):
             res, buf, ev = item
             ev.synchronize()
             host = buf[: res.out.shape[0]].numpy()
-            outs = [None] * len(res.perm)
-            for k, i in enumerate(res.perm):
-                outs[int(i)] = host[int(res.utt_frame_off[k]): int(res.utt_frame_off[k + 1])]
-            return outs
+            lo, hi = res.utt_frame_off[:-1].tolist(), res.utt_frame_off[1:].tolist()
+            return [host[lo[k]:hi[k]] for k in np.argsort(res.perm, kind="stable").tolist()]   # caller's order
 
-        # host planning (flattening ~1000 small arrays takes milliseconds) runs one or two batches ahead in a thread;
-        # numpy and the ctypes launches release the GIL, so it overlaps the launches of the current batch
+        # host planning (flattening ~1000 small arrays, ~2 ms) can run one or two batches ahead in a helper thread
+        # (numpy and the ctypes launches release the GIL). Measured on S batch 1024 it does not pay (5.52 vs 5.42 ms per
+        # batch inline: the host is already ahead of the GPU), so it is opt-in for slower hosts / larger batches.
         import queue
         import threading
         plans = queue.Queue(maxsize=2)
@@ -252,13 +252,14 @@ class Tacotron2_sa(_TTSBase, torch.nn.Module):
             except BaseException as e:                                 # re-raised in the consumer
                 plans.put(e)
 
-        threading.Thread(target=planner, daemon=True).start()
+        if planner_thread:
+            threading.Thread(target=planner, daemon=True).start()
+            plan_iter = iter(plans.get, None)
+        else:                                                         # plan on the calling thread, batch by batch
+            plan_iter = (self._plan(**(b if isinstance(b, dict) else {"xs": b})) for b in batches)
         engine = self.engine()
         n = 0
-        while True:
-            pl = plans.get()
-            if pl is None:
-                break
+        for pl in plan_iter:
             if isinstance(pl, BaseException):
                 raise pl
             if before_batch is not None:
