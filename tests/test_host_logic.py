@@ -62,6 +62,39 @@ def test_plan_packing_and_order():
         planmod.make_plan([np.arange(3)], f0s=[np.zeros(3)])
 
 
+def test_plan_matches_per_utterance_loop():
+    """make_plan (vectorised, int32 np.repeat arithmetic) against the obvious per-utterance loop, for ragged random
+    batches incl. lists / (N,1) columns as inputs, forced prosody and compensating length errors."""
+    rs = np.random.RandomState(7)
+    for B in (1, 2, 17, 64):
+        lens = rs.randint(1, 40, size=B)
+        xs = [rs.randint(1, 76, size=n) for n in lens]
+        ds = [rs.randint(1, 9, size=n) for n in lens]
+        f0 = [rs.randn(n).astype(np.float32) for n in lens]
+        en = [rs.randn(n, 1).astype(np.float32) for n in lens]            # (N, 1) columns take the slow path
+        ids = rs.permutation(1000)[:B]
+        pl = planmod.make_plan([x.tolist() if i % 3 == 0 else x for i, x in enumerate(xs)], ds, f0, en, utt_ids=ids)
+        order = sorted(range(B), key=lambda i: (-lens[i], i))
+        assert pl.perm.tolist() == order and pl.n_utts == B and pl.n_rows == int(lens.sum())
+        o = 0
+        for k, i in enumerate(order):
+            n = int(lens[i])
+            sl = slice(o, o + n)
+            assert pl.utt_off[k] == o and pl.utt_off[k + 1] == o + n
+            assert np.array_equal(pl.ids[sl], xs[i]) and np.array_equal(pl.dur[sl], ds[i])
+            assert np.array_equal(pl.pitch[sl], f0[i]) and np.array_equal(pl.energy[sl], en[i][:, 0])
+            assert (pl.row_utt[sl] == ids[i]).all() and np.array_equal(pl.row_phone[sl], np.arange(n))
+            assert (pl.seg_lo[sl] == o).all() and (pl.seg_hi[sl] == o + n).all()
+            o += n
+        for name in ("utt_off", "row_utt", "row_phone", "seg_lo", "seg_hi", "dur"):
+            assert getattr(pl, name).dtype == np.int32, name
+    # two length errors that cancel in the total must still be caught
+    with pytest.raises(ValueError):
+        planmod.make_plan([np.arange(1, 4), np.arange(1, 4)], [np.ones(4, int), np.ones(2, int)])
+    with pytest.raises(ValueError):
+        planmod.make_plan([np.arange(1, 4)], [np.array([1, -1, 2])])
+
+
 def test_shard_utterances_balanced_and_complete():
     rs = np.random.RandomState(0)
     costs = rs.randint(50, 1000, size=103)
