@@ -160,7 +160,7 @@ def workload(args, rank):
 def cpu_port_time(kind, xs, ds, budget_s, seed):
     """Time the oracle port (the reference's algorithm on torch CPU, per-utterance loop like
     tts.py:655-674) on a bounded sample. -> (frames/s, n_utts, frames, seconds, threads)"""
-    from oracle import restate          # CPU baseline leg: the only place bench.py touches oracle/
+    from oracle import restate          # CPU baseline leg: bench.py touches oracle/ only here and in parity_check
     torch.set_num_threads(os.cpu_count())
     sd = synth.random_state_dict(hparams.preset(kind), seed)
     drop = restate.Dropout(0.5, 1, native=True)       # torch's F.dropout, as the reference runs it
@@ -189,11 +189,13 @@ def run_reference(args, rank, world):
             vals.append(last)
     fps = sum(v[2] for v in vals) / sum(v[3] for v in vals)
     sample = f"first {vals[-1][1]} utterances ({vals[-1][2]} frames) of the batch-{args.batch} workload per step, per-utterance loop"
+    cfg = config_dict(args, world)
+    cfg["precision"] = "fp32 (torch CPU; the GPU arm of the same workload computes its GEMMs in bf16)"
     line = {
         "metric": "mel frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(v[3] for v in vals) / len(vals), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": config_dict(args, world),
+        "config": cfg,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": vals[-1][4], "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference is Python and cannot travel to the GPU box: this is oracle/restate.py, the op-for-op "
@@ -207,8 +209,173 @@ def config_dict(args, world):
                         f"utterances per GPU" + (" (500-phoneme stress)" if args.stress else ""),
             "model_size": args.model, "per_gpu_batch": args.batch, "global_batch": args.batch * world,
             "precision": args.precision, "prenet_dropout": args.dropout, "forced_durations": True,
-            "parallelism": f"utterance-sharded x{world}, no hot-path collective, final mel gather to rank 0",
-            "l2": "flushed between timed steps (256 MiB write, outside the per-step events)"}
+            "parallelism": f"utterance-sharded x{world}, no hot-path collective, final mel gather to rank 0"
+                           + (" pipelined across steps (the mels of step i travel while step i+1 computes)" if world > 1 else ""),
+            "l2": "flushed before every timed step (160 MiB write, INSIDE the timed region)"}
+
+
+FLUSH_BYTES = 160 << 20          # > the 126 MB L2
+
+
+class Arm:
+    """One benchmark configuration on this rank: model + engine + uploaded batch."""
+
+    def __init__(self, m, xs, ds, utt_ids=None, predicted=False):
+        from fcl_taco2_b200 import plan as planmod
+        self.m, self.eng, self.xs, self.ds = m, m.engine(), xs, ds
+        self.utt_ids = utt_ids
+        self.plan = planmod.make_plan(xs, None if predicted else ds, utt_ids=utt_ids)
+        self.n_rows = self.plan.n_rows
+        self.n_frames = int(sum(int(d.sum()) for d in ds)) if not predicted else None
+        self.dinp, self.h2d_bytes = self.eng.upload(self.plan)
+        self.bounds = None
+
+    def chunk_bounds(self, k):
+        from fcl_taco2_b200 import dist as fdist
+        per_utt = np.add.reduceat(self.plan.dur.astype(np.int64), self.plan.utt_off[:-1].astype(np.int64))
+        return fdist.chunk_bounds(np.concatenate([[0], np.cumsum(per_utt)]), k)
+
+
+def time_arm(arm, steps, warmup, dropout, flush, dist=None, dev=None, gather=None, k_chunks=0, sampler=None):
+    """W untimed + K timed passes of `arm`. The timed region is ONE bracket around the K passes (barrier +
+    synchronize on both sides, CUDA events on the launching stream): L2 flush + pass (+ the hand-over of the mels to the
+    pipelined gather) per step, and the wait for the last transfer at the end. Per-stage events inside give the
+    breakdown. -> dict(total_ms, stage_ms (per step), launches (per step), frames (per step), last result)"""
+    eng, m = arm.eng, arm.m
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_step(timed):
+        flush.fill_(1)
+        eng.stage_events = [] if timed else None
+        if gather is not None:
+            res = eng.run_uploaded(arm.plan, arm.dinp, m.hp.zoneout_rate, dropout, 1, out_chunks=k_chunks,
+                                   chunk_cb=gather.begin())
+        else:
+            res = eng.run_uploaded(arm.plan, arm.dinp, m.hp.zoneout_rate, dropout, 1)
+        se = eng.stage_events
+        eng.stage_events = None
+        return res, se
+
+    import gc
+    for _ in range(warmup):
+        one_step(False)
+    if gather is not None:
+        gather.drain()
+    gc.collect()
+    gc.disable()            # a host GC pause between launches would show up as GPU idle time inside the bracket
+    try:
+        barrier()
+        if sampler is not None:
+            sampler.mark()
+        launches0 = eng.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        stage_evs, res = [], None
+        for _ in range(steps):
+            res, se = one_step(True)
+            stage_evs.append(se)
+        bufs = None
+        if gather is not None:
+            t0 = torch.cuda.Event(enable_timing=True); t0.record()
+            bufs = gather.drain()          # only the LAST step's transfer is still in flight here
+            t1 = torch.cuda.Event(enable_timing=True); t1.record()
+            stage_evs.append([("gather_tail_total", t0, t1)])
+        e1.record()
+        barrier()
+    finally:
+        gc.enable()
+    stage_ms = {}
+    for se in stage_evs:
+        for name, a, b in se:
+            stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b) / steps
+    n_frames = arm.n_frames if arm.n_frames is not None else int(res.out.shape[0])
+    return dict(total_ms=float(e0.elapsed_time(e1)), stage_ms=stage_ms, launches=(eng.launches - launches0) / steps,
+                frames=n_frames, rows=arm.n_rows, res=res, bufs=bufs)
+
+
+def parity_check(arm, res, dropout, seed, n=8):
+    """Outside every timed region: `n` sampled utterances of the benchmark batch's LAST output against the oracle
+    (oracle/restate.py, fp32 CPU, same counter-based dropout mask). bench.py uses oracle/ only as this checker and as
+    the CPU baseline."""
+    from oracle import restate
+    outs = res.per_utterance()
+    sd = {k: v.detach().cpu() for k, v in arm.m.state_dict().items()}
+    rs = np.random.RandomState(1234)
+    order = np.argsort([-len(x) for x in arm.xs], kind="stable")
+    pick = sorted(set([int(order[0]), int(order[-1])] + rs.choice(len(arm.xs), min(n, len(arm.xs)), replace=False).tolist()))[:n]
+    mx, l1, cnt = 0.0, 0.0, 0
+    for i in pick:
+        uid = i if arm.utt_ids is None else int(arm.utt_ids[i])
+        ref = restate.inference(sd, torch.from_numpy(arm.xs[i]), dur=arm.ds[i], dropout=restate.Dropout(dropout, seed),
+                                utt_index=uid, fast_lstm=True)
+        diff = (outs[i].cpu() - ref).abs()
+        mx = max(mx, float(diff.max()))
+        l1 += float(diff.sum()); cnt += diff.numel()
+    return {"max_abs": mx, "mean_l1": l1 / max(cnt, 1), "n": len(pick), "against": "oracle/restate.py fp32 (CPU), same Philox "
+            "dropout mask; last output of the benchmark batch, checked outside the timed region"}
+
+
+def decoder_roofline(model, t, pk, traffic=None):
+    macs = MACS[model]
+    dec_ms = t["stage_ms"].get("decoder_loop", 0.0)
+    dec_flops = 2.0 * macs["decoder_row_step"] * t["frames"]
+    achieved = dec_flops / (dec_ms * 1e-3) / 1e12 if dec_ms > 0 else 0.0
+    return {"kernel": "decoder step loop (fcl_decoder_*), rank 0", "bound": "tensor", "achieved": achieved,
+            "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"], "traffic": traffic,
+            "peak_source": pk["src"] + " bf16_tflops (burst: one ~1-2 ms launch inside a 4 ms step at full clocks)",
+            "frac_of_sustained": achieved / pk["tf_sust"], "ms_per_launch": dec_ms,
+            "algorithmic_flops_per_launch": dec_flops,
+            "note": "algorithmic FLOPs = 2 x MAC per useful row-step (reference formulation, nothing hoisted) x frames"}
+
+
+def secondary_configs(args, dev, flush, pk):
+    """The other BASELINE.json configurations, driver-visible (value + decoder roofline fraction each): config 2
+    (T, batch 32), config 4 (500-phoneme stress batch) and the production path with PREDICTED durations (biased
+    duration head; the pass contains the one data-dependent D2H sync). 1 GPU, fewer steps."""
+    from fcl_taco2_b200 import model as M
+    out = {}
+    steps, warm = max(3, min(args.steps, 8)), 3
+
+    def entry(kind, t):
+        r = decoder_roofline(kind, t, pk)
+        return {"value": t["frames"] * steps / (t["total_ms"] * 1e-3), "unit": "frames/s", "ms_per_step": t["total_ms"] / steps,
+                "frames_per_step": t["frames"], "decoder_ms": r["ms_per_launch"], "decoder_tflops": r["achieved"],
+                "decoder_frac": r["frac"], "stage_ms_per_step": t["stage_ms"], "steps": steps}
+
+    # config 2: teacher, batch 32
+    mT = M.from_preset("T", seed=args.seed, device=dev, precision=args.precision).set_prenet_dropout(rate=args.dropout, seed=1)
+    xs, ds = synth.synth_batch(32, seed=args.seed + 5)
+    armT = Arm(mT, xs, ds)
+    t = time_arm(armT, steps, warm, args.dropout, flush, dev=dev)
+    out["T_batch32"] = entry("T", t)
+    out["T_batch32"]["parity"] = parity_check(armT, t["res"], args.dropout, 1, n=3)
+    del mT, armT, t
+    torch.cuda.empty_cache()
+    # config 4: stress, S, 64 utterances of 500 phonemes, skewed durations up to 40
+    mS = M.from_preset("S", seed=args.seed, device=dev, precision=args.precision).set_prenet_dropout(rate=args.dropout, seed=1)
+    xs, ds = synth.synth_batch(64, seed=args.seed + 6, stress=True, fixed_len=500)
+    armS = Arm(mS, xs, ds)
+    t = time_arm(armS, steps, warm, args.dropout, flush, dev=dev)
+    out["S_stress_500x64"] = entry("S", t)
+    out["S_stress_500x64"]["parity"] = parity_check(armS, t["res"], args.dropout, 1, n=2)
+    del armS, t
+    # production path: predicted durations (duration head biased so that a random-init model emits ~7 frames/phoneme)
+    sd = dict(mS.state_dict())
+    sd["duration_predictor.linear.bias"] = torch.full_like(sd["duration_predictor.linear.bias"], float(np.log(8.0)))
+    mP = M.from_preset("S", seed=None, device="cpu", precision=args.precision)
+    mP.load_state_dict(sd)
+    mP = mP.to(dev).set_prenet_dropout(rate=args.dropout, seed=1)
+    xs, ds = synth.synth_batch(args.batch, seed=args.seed)
+    armP = Arm(mP, xs, ds, predicted=True)
+    t = time_arm(armP, steps, warm, args.dropout, flush, dev=dev)
+    out["S_predicted_durations"] = entry("S", t)
+    out["S_predicted_durations"]["note"] = ("durations from the duration predictor (head bias log 8): includes the predictor, "
+                                            "the serialised length regulator and the D2H sync of the frame totals")
+    return out
 
 
 def main():
@@ -224,10 +391,11 @@ def main():
     ap.add_argument("--stress", action="store_true")
     ap.add_argument("--latency-utts", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip latency, secondary configs and the strong-scaling arm")
     ap.add_argument("--pair", type=int, default=-1, help="cta_group::2 decoder: 1 on, 0 off, -1 engine default")
     ap.add_argument("--e2e-planner", type=int, default=0, help="inference_stream: plan batches in a helper thread (1) or inline (0)")
     ap.add_argument("--dropout", type=float, default=0.5, help="prenet dropout rate (reference default 0.5)")
+    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "peer"], help="N > 1: transport of the final mel gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -240,12 +408,14 @@ def main():
 
     import torch.distributed as dist
     from fcl_taco2_b200 import model as M, plan as planmod, dist as fdist
+    prev_affinity = fdist.bind_to_gpu_numa_node(local)     # pinned staging buffers land on the GPU's own NUMA node
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/fcl_nccl_%h_%p.log")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
+    dgroup = dist if world > 1 else None
 
     m = M.from_preset(args.model, seed=args.seed, device=dev, precision=args.precision)
     m.set_prenet_dropout(rate=args.dropout, seed=1)
@@ -253,75 +423,40 @@ def main():
     if args.pair >= 0:
         eng.use_pair = bool(args.pair)
     xs, ds = workload(args, rank)
-    pl = planmod.make_plan(xs, ds)
-    n_frames = int(sum(int(d.sum()) for d in ds))
-    n_rows = pl.n_rows
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    dinp, h2d_bytes = eng.upload(pl)
+    arm = Arm(m, xs, ds)
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    pk = peaks()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    # groups of utterances whose mels are sent while the next group's postnet runs; splitting the fused postnet costs
-    # ~0.2 ms, which only pays once the gather (bound by rank 0's ingress, (N-1) x 185 MB) is longer than that
+    # groups of utterances whose mels are handed to the gather while the next group's postnet runs
     K_CHUNKS = 1 if world <= 2 else 4
-    gather = None
-    if world > 1:   # forced durations: every rank's output chunk boundaries are known (and exchanged) before the pass
-        from fcl_taco2_b200.plan import output_chunks
-        per_utt = np.add.reduceat(pl.dur.astype(np.int64), pl.utt_off[:-1].astype(np.int64))
-        ch = output_chunks(np.concatenate([[0], np.cumsum(per_utt)]), K_CHUNKS)
-        bounds = [c[2] for c in ch] + [ch[-1][3]]
-        bounds += [bounds[-1]] * (K_CHUNKS + 1 - len(bounds))
-        gather = fdist.ChunkedGather(bounds, m.odim, dev)
+    make_gather = lambda a: fdist.make_gather(a.chunk_bounds(K_CHUNKS), m.odim, dev, kind=args.gather) if world > 1 else None
 
-    def one_step(timed):
-        flush.fill_(rank + 1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        eng.stage_events = [] if timed else None
-        e0.record()
-        if world > 1:
-            res = eng.run_uploaded(pl, dinp, m.hp.zoneout_rate, args.dropout, 1, out_chunks=K_CHUNKS, chunk_cb=gather.on_chunk)
-            with eng.stage("gather_tail"):
-                gather.finish()            # transfers were started chunk by chunk during the postnet
-        else:
-            res = eng.run_uploaded(pl, dinp, m.hp.zoneout_rate, args.dropout, 1)
-        e1.record()
-        return e0, e1, None, eng.stage_events, None    # results are dropped: holding K outputs alive would force a
-                                                       # fresh cudaMalloc of the output buffer inside every timed step
-
-    import gc
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        one_step(False)
-    if rank == 0:
         t_wait = time.time()
         while not sampler.ready() and time.time() - t_wait < 3.0:
             time.sleep(0.02)                       # the sampler is up and polling before the timed region starts
-    gc.collect()
-    gc.disable()            # a host GC pause between launches would show up as GPU idle time inside the events
-    barrier()
-    sampler.mark()
-    launches0 = eng.launches
-    evs = [one_step(True) for _ in range(args.steps)]
-    barrier()
-    launches = eng.launches - launches0
+    gather = make_gather(arm)
+    t = time_arm(arm, args.steps, args.warmup, args.dropout, flush, dgroup, dev, gather, K_CHUNKS, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
-    step_ms = [e0.elapsed_time(e1) for e0, e1, *_ in evs]
-    total_ms = float(sum(step_ms))
-    stage_ms = {}
-    for _, _, _, se, _ in evs:
-        for name, a, b in se:
-            stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b)
-    eng.stage_events = None
+    total_ms, stage_ms, n_frames, n_rows = t["total_ms"], t["stage_ms"], t["frames"], t["rows"]
+    parity = parity_check(arm, t["res"], args.dropout, 1) if rank == 0 else None
+    gather_kind = gather.kind if gather is not None else None
+    if gather is not None:
+        gather.close()
+    del gather
+    t["res"] = t["bufs"] = None
 
     # ---- e2e through the public API: host ids/durations in, host mels out. model.inference_stream() is the call a
     # decode driver makes: every batch is planned on the host, uploaded, decoded, and its mels are copied to pinned host
     # memory on a copy stream while the next batch computes. The timed region covers K whole batches, from the first
     # upload to the arrival of the last batch's mels on the host (L2 flushed before every batch, inside the region).
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
     def batches(k):
         for _ in range(k):
             yield {"xs": xs, "durs": ds}
@@ -339,22 +474,48 @@ def main():
     assert got == args.steps * len(xs)
     e2e_ms = float(e0.elapsed_time(e1))
 
+    # ---- strong scaling (BASELINE config 3 as written: ONE batch of `--batch` utterances sharded over the N GPUs)
+    strong = None
+    if world > 1 and not args.no_extra:
+        gxs, gds = workload(args, 0)                                  # the same global batch on every rank
+        shards = planmod.shard_utterances([int(d.sum()) for d in gds], world)
+        mine = shards[rank]
+        sarm = Arm(m, [gxs[i] for i in mine], [gds[i] for i in mine], utt_ids=mine)
+        sg = make_gather(sarm)
+        st = time_arm(sarm, args.steps, args.warmup, args.dropout, flush, dgroup, dev, sg, K_CHUNKS)
+        ts = torch.tensor([st["total_ms"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        shard_equal = None
+        if rank == 0:
+            # determinism check: the gathered shards must equal, bit for bit, the whole batch decoded on ONE GPU
+            full = m.inference_batch(gxs, durs=gds)
+            shard_equal = True
+            for r in range(world):
+                rp = planmod.make_plan([gxs[i] for i in shards[r]], [gds[i] for i in shards[r]], utt_ids=shards[r])
+                buf = st["res"].out if r == 0 else st["bufs"][r]
+                fo = np.concatenate([[0], np.cumsum([int(gds[shards[r][int(j)]].sum()) for j in rp.perm])])
+                for k, j in enumerate(rp.perm):
+                    shard_equal = shard_equal and torch.equal(buf[int(fo[k]):int(fo[k + 1])], full[shards[r][int(j)]])
+            del full
+        tot_frames = float(sum(int(d.sum()) for d in gds))
+        strong = {"scaling": "strong", "global_batch": args.batch, "value": tot_frames * args.steps / (float(ts[0]) * 1e-3),
+                  "unit": "frames/s", "ms_per_step": float(ts[0]) / args.steps, "frames_per_step": tot_frames,
+                  "shard_equal": shard_equal, "stage_ms_per_step_rank0": st["stage_ms"],
+                  "note": "same kernels, one batch of --batch utterances LPT-sharded by frame count; gather to rank 0 pipelined across steps"}
+        sg.close()
+        del sg, st, sarm
+
     # ---- reduce over ranks: max time, sum frames
-    t = torch.tensor([total_ms, e2e_ms, float(n_frames), float(n_rows), float(launches)], dtype=torch.float64, device=dev)
+    tt = torch.tensor([total_ms, e2e_ms, float(n_frames), float(n_rows), float(t["launches"])], dtype=torch.float64, device=dev)
     if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         total_ms, e2e_ms = float(tmax[0]), float(tmax[1])
-        all_frames, all_rows, all_launches = float(tsum[2]), float(tsum[3]), int(tsum[4])
+        all_frames, all_rows, all_launches = float(tsum[2]), float(tsum[3]), float(tsum[4])
     else:
-        all_frames, all_rows, all_launches = float(n_frames), float(n_rows), launches
+        all_frames, all_rows, all_launches = float(n_frames), float(n_rows), float(t["launches"])
 
     if rank == 0:
-        pk = peaks()
-        macs = MACS[args.model]
-        dec_ms = stage_ms.get("decoder_loop", 0.0) / args.steps
-        dec_flops = 2.0 * macs["decoder_row_step"] * n_frames
-        achieved = dec_flops / (dec_ms * 1e-3) / 1e12 if dec_ms > 0 else 0.0
         value = all_frames * args.steps / (total_ms * 1e-3)
         traffic = None
         try:
@@ -370,22 +531,23 @@ def main():
             "frames_per_step": all_frames, "phoneme_rows_per_step": all_rows,
             "clocks": clocks,
             "e2e": {"value": all_frames * args.steps / (e2e_ms * 1e-3), "unit": "frames/s",
-                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(n_frames * m.odim * 4),
+                    "h2d_bytes_per_step": int(arm.h2d_bytes), "d2h_bytes_per_step": int(n_frames * m.odim * 4),
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": all_launches,
-            "roofline": {"kernel": "decoder step loop (fcl_decoder_*), rank 0", "bound": "tensor", "achieved": achieved,
-                         "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"], "traffic": traffic,
-                         "peak_source": pk["src"] + " bf16_tflops_sustained", "ms_per_launch": dec_ms,
-                         "algorithmic_flops_per_launch": dec_flops,
-                         "note": "algorithmic FLOPs = 2 x MAC per useful row-step (reference formulation, nothing hoisted) x frames"},
-            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+            "gpu_launches": int(round(all_launches * args.steps)),
+            "parity": parity,
+            "roofline": decoder_roofline(args.model, t, pk, traffic),
+            "stage_ms_per_step": stage_ms,
         }
+        if gather_kind:
+            line["gather"] = gather_kind
+        if strong is not None:
+            line["strong"] = strong
         # the HBM-side view SURVEY 8(d) asks for next to the tensor roofline: algorithmic bytes / stage time, rank 0
         sec = []
         for name, key, nbytes in (("postnet (first input + last output only: 640 B/frame)", "postnet", 640.0 * n_frames),
                                   ("length regulator scan + frame map (8 B/phoneme + 20 B/frame)", None,
                                    8.0 * n_rows + 20.0 * n_frames)):
-            ms = (stage_ms.get(key, 0.0) if key else stage_ms.get("len_reg", 0.0) + stage_ms.get("frame_map", 0.0)) / args.steps
+            ms = stage_ms.get(key, 0.0) if key else stage_ms.get("len_reg", 0.0) + stage_ms.get("frame_map", 0.0)
             if ms > 0:
                 gbs = nbytes / (ms * 1e-3) / 1e9
                 sec.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
@@ -393,7 +555,14 @@ def main():
         line["roofline_secondary"] = sec
         if not args.no_extra:
             line["p50_utt_latency_ms"] = latency_p50(m, args, dev)
+            if world == 1 and not args.stress and args.model == "S":
+                try:
+                    line["secondary"] = secondary_configs(args, dev, flush, pk)
+                except Exception as e:           # never lose the headline line to a secondary configuration
+                    line["secondary"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only (torchrun pins OMP threads to 1)
+            if prev_affinity:
+                os.sched_setaffinity(0, prev_affinity)   # the CPU baseline gets every host core, not just the GPU's NUMA node
             fps, n, fr, dt, thr = cpu_port_time(args.model, xs, ds, budget_s=15.0, seed=args.seed)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": thr, "kind": "port",
                                     "sample": f"first {n} utterances ({fr} frames) of the same workload, per-utterance "

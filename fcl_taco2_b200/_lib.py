@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -134,7 +134,8 @@ ENTRY_POINTS = {
     "fcl_conv_stack_bf16": ConvStackParams,
 }
 PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_last_error", "fcl_sm_count", "fcl_struct_size",
-                 "fcl_decoder_bf16_workspace"]
+                 "fcl_decoder_bf16_workspace", "fcl_peer_alloc", "fcl_peer_free", "fcl_ipc_export", "fcl_ipc_open",
+                 "fcl_ipc_close", "fcl_copy_async", "fcl_wait_flags", "fcl_write_flags"]
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 MAX_DURATION = 1023
@@ -174,8 +175,25 @@ def load():
     lib.fcl_decoder_bf16_workspace.restype = C.c_int
     lib.fcl_decoder_bf16_workspace.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                                C.POINTER(C.c_int64)]
+    for name, argtypes in (("fcl_peer_alloc", [C.c_int64, C.POINTER(C.c_void_p)]), ("fcl_peer_free", [C.c_void_p]),
+                           ("fcl_ipc_export", [C.c_void_p, C.c_char_p]), ("fcl_ipc_open", [C.c_char_p, C.POINTER(C.c_void_p)]),
+                           ("fcl_ipc_close", [C.c_void_p]),
+                           ("fcl_copy_async", [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+                           ("fcl_wait_flags", [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+                           ("fcl_write_flags", [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p])):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = argtypes
     _lib = lib
     return lib
+
+
+def plain(name: str, *args):
+    """Invoke one of the non-struct entry points (peer-memory plumbing); raise FclError on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise FclError(f"{name} failed ({rc}): {lib.fcl_last_error().decode()}")
 
 
 def call(name: str, params, stream: int):

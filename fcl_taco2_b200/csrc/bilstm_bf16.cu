@@ -274,12 +274,7 @@ extern "C" int fcl_bilstm_bf16(const FclBiLstmBf16Params* p, void* stream) {
   const int stages = p->hidden <= 128 ? 4 : 3;
   const size_t smem = (size_t)stages * kBlBBytes + 2 * (size_t)p->hidden * 256;
   FCL_REQUIRE(smem <= 226 * 1024, "shared memory budget exceeded");
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(bilstm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("fcl_bilstm_bf16: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
-    attr_smem = smem;
-  }
+  if (int rc = ensure_dyn_smem(bilstm_bf16_kernel, smem, "fcl_bilstm_bf16")) return rc;
   FCL_REQUIRE(p->tile_utts == 32 || p->tile_utts == 64 || p->tile_utts == 128, "tile_utts must be 32, 64 or 128");
   dim3 grid((p->n_utts + p->tile_utts - 1) / p->tile_utts, 2);
   bilstm_bf16_kernel<<<grid, kBlThreads, smem, as_stream(stream)>>>(*p, stages);

@@ -17,6 +17,21 @@ int check_launch(const char* what);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember what was set per (kernel, device)
+// so that a second GPU in the same process (or a model on cuda:1 while cuda:0 is current elsewhere) gets it too.
+template <typename Kernel>
+static inline int ensure_dyn_smem(Kernel kernel, size_t bytes, const char* what) {
+  static int have[64] = {0};                      // one table per kernel instantiation; benign race: worst case it is set twice
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess && (dev < 0 || dev >= 64 || have[dev] < (int)bytes)) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) have[dev] = (int)bytes;
+  }
+  if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return FCL_ECUDA; }
+  return FCL_OK;
+}
+
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ---- Philox4x32-10 (Salmon et al. SC'11); CPU twin: oracle/philox.py ------------------------

@@ -286,12 +286,7 @@ extern "C" int fcl_conv_stack_bf16(const FclConvStackParams* p, void* stream) {
   b_stages = b_stages > kCsMaxBStages ? kCsMaxBStages : b_stages;
   const size_t smem = img_bytes + (size_t)b_stages * b_slot;
   if (smem > 216 * 1024) { set_error("fcl_conv_stack_bf16: %zu B shared memory needed (channels too wide to fuse)", smem); return FCL_EUNSUPPORTED; }
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_stack_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-    if (e != cudaSuccess) { set_error("fcl_conv_stack_bf16: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
-    attr_done = true;
-  }
+  if (int rc = ensure_dyn_smem(conv_stack_bf16_kernel, 216 * 1024, "fcl_conv_stack_bf16")) return rc;
   conv_stack_bf16_kernel<<<p->n_tiles, kCsThreads, smem, as_stream(stream)>>>(*p, (uint32_t)img_bytes, (uint32_t)b_slot,
                                                                                tmem_cols_pow2((uint32_t)max_cout), b_stages);
   return check_launch("fcl_conv_stack_bf16");

@@ -569,12 +569,7 @@ extern "C" int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream) {
   FCL_REQUIRE(p->n_slots >= 1, "n_slots must be >= 1");
   FCL_REQUIRE(p->zoneout >= 0.f && p->zoneout < 1.f && p->dropout_p >= 0.f && p->dropout_p < 1.f, "bad rates");
   const size_t smem = (size_t)kDbStages * kStageBytes;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(decoder_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("fcl_decoder_bf16: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
-    attr_done = true;
-  }
+  if (int rc = ensure_dyn_smem(decoder_bf16_kernel, smem, "fcl_decoder_bf16")) return rc;
   // n_slots CTAs = n_slots / group groups; the spin barriers of group mode need every CTA resident: one CTA per SM,
   // n_slots <= SM count (checked by the caller against fcl_sm_count()).
   cudaError_t e = cudaMemsetAsync(p->group_sync, 0, sizeof(int32_t) * 2 * (size_t)(p->n_slots / p->group), as_stream(stream));

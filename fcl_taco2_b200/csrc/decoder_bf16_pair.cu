@@ -578,12 +578,7 @@ extern "C" int fcl_decoder_bf16_pair(const FclDecoderBf16Params* p, void* stream
   FCL_REQUIRE(p->zoneout >= 0.f && p->zoneout < 1.f && p->dropout_p >= 0.f && p->dropout_p < 1.f, "bad rates");
   FCL_REQUIRE((long long)((p->n_tiles + 1) / 2) <= (long long)kDbMaxTilesPerCta * (p->n_slots / 2), "too many tiles");
   const size_t smem = (size_t)kDbStages * kStageBytes;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(decoder_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("fcl_decoder_bf16_pair: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
-    attr_done = true;
-  }
+  if (int rc = ensure_dyn_smem(decoder_bf16_pair_kernel, smem, "fcl_decoder_bf16_pair")) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)p->n_slots);
   cfg.blockDim = dim3(kDbThreads);

@@ -316,12 +316,7 @@ extern "C" int fcl_conv_gemm_bf16(const FclConvGemmBf16Params* p, void* stream) 
   FCL_REQUIRE(b_stages >= 2, "tile too large for two weight stages");
   size_t smem = a_stages * a_bytes + b_stages * b_bytes;
   if (smem < 4 * 32 * 68 * sizeof(float)) smem = 4 * 32 * 68 * sizeof(float);   // epilogue staging patches
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
-    if (e != cudaSuccess) { set_error("fcl_conv_gemm_bf16: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
-    attr_done = true;
-  }
+  if (int rc = ensure_dyn_smem(conv_gemm_bf16_kernel, 216 * 1024, "fcl_conv_gemm_bf16")) return rc;
   const int tiles = p->tile_src ? p->n_tiles : (p->rows + 127) / 128;
   dim3 grid(tiles, p->cout / p->ntile);
   conv_gemm_bf16_kernel<<<grid, kGemmThreads, smem, as_stream(stream)>>>(*p, a_stages, b_stages);

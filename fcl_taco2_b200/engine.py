@@ -52,7 +52,13 @@ class Engine:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.FclError("the B200 path runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         _lib.load()
+        with torch.cuda.device(self.device):      # fcl_sm_count() and the kernels' per-device attributes use the CURRENT device
+            self._init_device_state(hp, packed, precision, bf16_gemms, bf16_decoder)
+
+    def _init_device_state(self, hp, packed, precision, bf16_gemms, bf16_decoder):
         self.w = {k: v.to(self.device) for k, v in packed.items()}
         self.wb = {}
         if precision == "bf16":
@@ -77,6 +83,7 @@ class Engine:
         self._stream_handle = None
         self.force_group = 0             # decoder group size override (tests); 0 = choose from the tile count
         self.use_pair = None             # cta_group::2 decoder (CTA pairs): None = when every SM has a tile anyway; True / False force it
+        self.skip_zero_durations = False # extension: phonemes with d = 0 produce no frames (the reference's inference asserts)
         self.use_encoder_stack = False   # measured: with 256 channels only a 2-stage weight ring fits beside the images
         self.stage_events = None      # when a list: (stage, start_event, stop_event) appended per stage (bench.py)
 
@@ -431,7 +438,10 @@ class Engine:
         parts = [("ids", plan.ids.view(np.int32)), ("utt_off", plan.utt_off), ("row_utt", plan.row_utt),
                  ("row_phone", plan.row_phone), ("seg_lo", plan.seg_lo), ("seg_hi", plan.seg_hi)]
         if plan.dur is not None:
-            parts.append(("dur", np.minimum(plan.dur, _lib.MAX_DURATION).astype(np.int32)))
+            if plan.dur.size and int(plan.dur.max()) > _lib.MAX_DURATION:
+                raise ValueError(f"duration {int(plan.dur.max())} exceeds the supported maximum of {_lib.MAX_DURATION} frames "
+                                 "per phoneme (FCL_MAX_DURATION; the reference's data cap is 50, preprocess.py:203)")
+            parts.append(("dur", plan.dur.astype(np.int32, copy=False)))
         if plan.pitch is not None:
             parts.append(("pitch", plan.pitch.view(np.int32)))
             parts.append(("energy", plan.energy.view(np.int32)))
@@ -479,8 +489,9 @@ class Engine:
     @torch.no_grad()
     def run(self, plan: BatchPlan, zoneout: float, dropout_p: float, dropout_seed: int,
             extras: bool = False, tile_rows=None) -> BatchResult:
-        d, h2d = self.upload(plan)
-        return self.run_uploaded(plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d)
+        with torch.cuda.device(self.device):
+            d, h2d = self.upload(plan)
+            return self.run_uploaded(plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d)
 
     @torch.no_grad()
     def run_uploaded(self, plan: BatchPlan, d: dict, zoneout: float, dropout_p: float, dropout_seed: int,
@@ -488,7 +499,8 @@ class Engine:
         """The pass proper, inputs already resident on the device (`d` from `upload`)."""
         self._arena_seq, self._in_pass = 0, not extras     # extras (tests) keep intermediates: no recycling
         try:
-            return self._run_uploaded(plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d, out_chunks, chunk_cb)
+            with torch.cuda.device(self.device):           # launches go to the engine's device whatever is current outside
+                return self._run_uploaded(plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d, out_chunks, chunk_cb)
         finally:
             self._in_pass = False
             self._stream_handle = None
@@ -520,10 +532,11 @@ class Engine:
 
         lr = None
         if not need_pred_dur:
-            if (plan.dur == 0).any():
+            if not self.skip_zero_durations and (plan.dur == 0).any():
                 raise ValueError("zero durations are outside the reference's working domain "
-                                 "(nets/modules/decoder_sa.py:575)")
-            per_utt = np.add.reduceat(np.minimum(plan.dur, _lib.MAX_DURATION).astype(np.int64), plan.utt_off[:-1].astype(np.int64))
+                                 "(nets/modules/decoder_sa.py:575); skip_zero_durations=True drops those phonemes from "
+                                 "the decoder the way the reference's forward() does (decoder_sa.py:459-463)")
+            per_utt = np.add.reduceat(plan.dur.astype(np.int64), plan.utt_off[:-1].astype(np.int64))
             ufo = np.concatenate([[0], np.cumsum(per_utt)])
             F = int(ufo[-1])
             use_side = P >= 4096                           # tiny batches: the cross-stream hand-over costs more than it hides
@@ -553,9 +566,14 @@ class Engine:
             frame_off, utt_frame_off, order, totals, sched, _, _, _ = length_regulation(dur, None)
             host = torch.cat([totals, utt_frame_off]).cpu().numpy()      # the one data-dependent D2H sync
             F, ufo = int(host[0]), host[2:].astype(np.int64)
-            if int((dur == 0).sum()) != 0:
+            if int(host[1]) >= _lib.MAX_DURATION:
+                raise ValueError(f"a predicted duration reached the supported maximum of {_lib.MAX_DURATION} frames per "
+                                 "phoneme (FCL_MAX_DURATION): the reference has no cap, refusing to truncate silently")
+            if not self.skip_zero_durations and int((dur == 0).sum()) != 0:
                 raise ValueError("predicted zero durations: outside the reference's working domain "
-                                 "(nets/modules/decoder_sa.py:575); pass dur=")
+                                 "(nets/modules/decoder_sa.py:575); pass dur= or skip_zero_durations=True")
+            if F == 0:
+                raise ValueError("every predicted duration is zero: no frames to decode")
             with self.stage("frame_map"):
                 fmap, pos = self.frame_map(frame_off, utt_frame_off, P, B, F, want_position=extras)
                 ftiles = self.conv_tiles(utt_frame_off, B, (F + 127) // 128 + B)

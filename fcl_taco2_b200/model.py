@@ -129,7 +129,7 @@ class Tacotron2_sa(_TTSBase, torch.nn.Module):
             _register(self, name, t, is_buf)
         self._engine = None
         self._dropout_rate = float(self.hp.dropout_rate)     # prenet dropout is ON at inference (decoder_sa.py:156-157)
-        self._dropout_seed = 0
+        self._dropout_seed = None                             # a fresh mask per call, like the reference's F.dropout
         self._calls = itertools.count()
         self.eval()
 
@@ -173,8 +173,9 @@ class Tacotron2_sa(_TTSBase, torch.nn.Module):
 
     # ------------------------------------------------------------------ dropout policy
     def set_prenet_dropout(self, rate=None, seed=None):
-        """rate 0 -> deterministic (exact-parity mode); default rate = conf dropout-rate (0.5), the
-        reference's behaviour. `seed` fixes the counter-based mask; None -> a fresh seed per call."""
+        """rate 0 -> deterministic (exact-parity mode); default rate = conf dropout-rate (0.5) with a fresh mask on
+        every call, the reference's behaviour (decoder_sa.py:156-157). `seed` (an int) fixes the counter-based mask for
+        reproducible output (tests, bench); None -> a fresh seed per call."""
         if rate is not None:
             if not 0.0 <= rate < 1.0:
                 raise ValueError("dropout rate must be in [0, 1)")
@@ -203,11 +204,20 @@ class Tacotron2_sa(_TTSBase, torch.nn.Module):
         return pl
 
     @torch.no_grad()
-    def inference_batch(self, xs, durs=None, f0s=None, energies=None, utt_ids=None, return_result=False):
+    def inference_batch(self, xs, durs=None, f0s=None, energies=None, utt_ids=None, return_result=False,
+                        skip_zero_durations=False):
         """Batched form of `inference`: xs is a list of 1-D id sequences (LongTensor / ndarray / list).
-        -> list of (L_i, odim) float32 tensors on the model device, in the order given."""
+        -> list of (L_i, odim) float32 tensors on the model device, in the order given.
+        `skip_zero_durations=True` (extension; the reference's inference asserts, decoder_sa.py:575): phonemes whose
+        forced or predicted duration is 0 still feed the encoder / predictors / prosody embeddings but get no decoder
+        row and no frames -- the semantics of the reference's teacher-forced forward() (decoder_sa.py:459-463)."""
         pl = self._plan(xs, durs, f0s, energies, utt_ids)
-        res = self.engine().run(pl, self.hp.zoneout_rate, self._dropout_rate, self._seed_for_call())
+        eng = self.engine()
+        eng.skip_zero_durations = bool(skip_zero_durations)
+        try:
+            res = eng.run(pl, self.hp.zoneout_rate, self._dropout_rate, self._seed_for_call())
+        finally:
+            eng.skip_zero_durations = False
         return res if return_result else res.per_utterance()
 
     @torch.no_grad()

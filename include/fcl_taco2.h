@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 14
+#define FCL_ABI_VERSION 15
 
 enum {
   FCL_OK = 0,
@@ -365,6 +365,24 @@ int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream);
  * n_slots = number of pairs), act_shared holds n_slots * shared_bytes_per_group, and w_stream uses the pair packing
  * (pack.py: pack_decoder_stream(pair=True): each stage block = [half 0][half 1], feat_out columns padded to 128). */
 int fcl_decoder_bf16_pair(const FclDecoderBf16Params* p, void* stream);
+
+/* ---------------------------------------------------------------- multi-GPU: peer-memory gather plumbing
+ * The path shards by utterance with no collective on the hot path; the one exchange is the final
+ * gather of the ragged mels to the root GPU. These entry points move it onto the copy engines: the root allocates
+ * receive buffers (fcl_peer_alloc) and exports them (fcl_ipc_export, a 64-byte cudaIpcMemHandle_t); every other rank
+ * maps them (fcl_ipc_open, from ITS device) and pushes finished mels with fcl_copy_async on a side stream -- DMA over
+ * NVLink, no SM taken from the next pass. Hand-shakes are 32-bit flags in exported memory: fcl_write_flags stores
+ * `value` into n flags, fcl_wait_flags makes `stream` wait until n flags equal `expect` (a one-warp polling kernel).
+ * No reference counterpart (the reference decodes one utterance at a time on one device: tts.py:655-674).
+ */
+int fcl_peer_alloc(int64_t bytes, void** dptr);
+int fcl_peer_free(void* dptr);
+int fcl_ipc_export(void* dptr, uint8_t* handle64);
+int fcl_ipc_open(const uint8_t* handle64, void** dptr);
+int fcl_ipc_close(void* dptr);
+int fcl_copy_async(void* dst, const void* src, int64_t bytes, void* stream);
+int fcl_wait_flags(const int32_t* flags, int32_t n, int32_t expect, void* stream);
+int fcl_write_flags(int32_t* flags, int32_t n, int32_t value, void* stream);
 
 #ifdef __cplusplus
 }

@@ -140,3 +140,37 @@ def test_inference_stream_matches_inference_batch():
             assert a.shape == b.shape and np.array_equal(a, b)
         n += 1
     assert n == len(sets)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_zero_duration_phonemes_are_skipped(precision):
+    """Extension: d = 0 phonemes feed the encoder / predictors / prosody embeddings but produce no
+    decoder row and no frames, as in the reference's forward() (decoder_sa.py:459-463). Without the opt-in the call
+    raises like the reference's assert (decoder_sa.py:575). Also: durations above FCL_MAX_DURATION raise (no clamp)."""
+    from fcl_taco2_b200 import model as M
+    m = M.from_preset("S", seed=None, device="cpu", precision=precision)
+    m.load_state_dict(weights("S", 4))
+    m = m.to("cuda:0").set_prenet_dropout(rate=0.5, seed=21)
+    xs, ds = synth.synth_batch(5, 91, fixed_len=37)
+    ds = [d.copy() for d in ds]
+    ds[0][[0, 5, 6, 7, 36]] = 0                 # first, a run, last
+    ds[1][::2] = 0                              # every other phoneme
+    ds[2][:] = 0; ds[2][18] = 4                 # a single voiced phoneme
+    ds[3][:] = 0                                # an utterance that produces no frames at all
+    with pytest.raises(ValueError):
+        m.inference_batch(xs, durs=ds)
+    outs = m.inference_batch(xs, durs=ds, skip_zero_durations=True)
+    sd = weights("S", 4)
+    tol = (MAX_ABS, MEAN_L1) if precision == "fp32" else (1.2e-1, 1.2e-2)
+    for i in range(5):
+        assert outs[i].shape == (int(ds[i].sum()), 80)
+        if ds[i].sum() == 0:
+            continue
+        ref = restate.inference(sd, torch.from_numpy(xs[i]), dur=ds[i], dropout=restate.Dropout(0.5, 21), utt_index=i,
+                                skip_zero=True)
+        mx, mean = err(outs[i].cpu(), ref)
+        assert mx < tol[0] and mean < tol[1], (i, mx, mean)
+    big = [d.copy() for d in ds]
+    big[4][3] = 1024
+    with pytest.raises(ValueError, match="exceeds the supported maximum"):
+        m.inference_batch(xs, durs=big, skip_zero_durations=True)
