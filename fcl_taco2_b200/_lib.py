@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -99,7 +99,23 @@ class DecoderBf16Params(C.Structure):
 
 class BiLstmBf16Params(C.Structure):
     _fields_ = [("n_utts", i32), ("hidden", i32), ("tile_utts", i32), ("utt_off", ptr), ("gx", ptr),
-                ("whh_packed", ptr), ("c_ws", ptr), ("out", ptr)]
+                ("whh_packed", ptr), ("c_ws", ptr), ("out", ptr), ("gx_blk", ptr), ("prow_off", ptr), ("gx_rows", i32)]
+
+
+class PadRowsParams(C.Structure):
+    _fields_ = [("n_utts", i32), ("n_rows", i32), ("gap", i32), ("utt_off", ptr), ("n_tiles", i32), ("prow_src", ptr),
+                ("prow_off", ptr)]
+
+
+class RowsToImageParams(C.Structure):
+    _fields_ = [("n_tiles", i32), ("chans", i32), ("src", ptr), ("ld", i32), ("gather", ptr), ("prow_src", ptr), ("img", ptr)]
+
+
+class ConvImgParams(C.Structure):
+    _fields_ = [("n_tiles", i32), ("cin", i32), ("cout", i32), ("taps", i32), ("nb", i32), ("act", i32), ("epi", i32),
+                ("in_img", ptr), ("w_packed", ptr), ("bias", ptr), ("prow_src", ptr), ("out_img", ptr), ("out_blk", ptr),
+                ("gamma", ptr), ("beta", ptr), ("head_w", ptr), ("head_b", f32), ("head_out", ptr), ("dur_out", ptr),
+                ("n_pairs", i32)]
 
 
 class DecoderScheduleParams(C.Structure):
@@ -113,7 +129,7 @@ class PackRowsParams(C.Structure):
 
 STRUCTS = [LenRegParams, FrameMapParams, ConvGemmParams, LayerNormParams, EmbedAddParams, BiLstmParams,
            DecoderParams, ConvGemmBf16Params, DecoderBf16Params, PackRowsParams, BiLstmBf16Params, ConvTilesParams, DecoderScheduleParams, ConvStackTilesParams,
-           ConvStackParams]
+           ConvStackParams, PadRowsParams, RowsToImageParams, ConvImgParams]
 
 ENTRY_POINTS = {
     "fcl_len_reg_scan": LenRegParams,
@@ -132,12 +148,17 @@ ENTRY_POINTS = {
     "fcl_decoder_bf16_pair": DecoderBf16Params,
     "fcl_conv_stack_tiles": ConvStackTilesParams,
     "fcl_conv_stack_bf16": ConvStackParams,
+    "fcl_pad_rows": PadRowsParams,
+    "fcl_rows_to_image": RowsToImageParams,
+    "fcl_conv_img_bf16": ConvImgParams,
 }
 PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_last_error", "fcl_sm_count", "fcl_struct_size",
                  "fcl_decoder_bf16_workspace", "fcl_peer_alloc", "fcl_peer_free", "fcl_ipc_export", "fcl_ipc_open",
                  "fcl_ipc_close", "fcl_copy_async", "fcl_wait_flags", "fcl_write_flags"]
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+EPI_IMAGE, EPI_LN_IMAGE, EPI_LN_HEAD, EPI_BLOCKED_F32 = 0, 1, 2, 3
+PAD_GAP = 2            # zero rows between utterances in the padded row space (halo of the k <= 5 convolutions)
 MAX_DURATION = 1023
 
 

@@ -24,6 +24,27 @@ constexpr int kBlThreads = 640;
 constexpr int kBlEpiThreads = 512;
 constexpr uint32_t kBlBBytes = 256u * 64u * 2u;          // one W_hh stage: 256 gate columns x 64 k
 
+// 16 consecutive gate-interleaved columns (4 hidden units x i,f,g,o) of the input projection of one phoneme:
+// either bf16 rows (P, 8H) or the fp32 column-blocked image [8H/16][gx_rows][16] in the padded row space.
+__device__ __forceinline__ void load_gx16(const FclBiLstmBf16Params& p, long row, long prow, int col, float (&g)[16]) {
+  if (p.gx_blk) {
+    const float4* s = reinterpret_cast<const float4*>(p.gx_blk + ((size_t)(col >> 4) * (size_t)p.gx_rows + (size_t)prow) * 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float4 v = __ldg(s + k); g[4 * k] = v.x; g[4 * k + 1] = v.y; g[4 * k + 2] = v.z; g[4 * k + 3] = v.w; }
+  } else {
+    const uint4* s = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.gx) + (size_t)row * (size_t)(8 * p.hidden) + col);
+    const uint4 a = __ldg(s), b = __ldg(s + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { g[2 * k] = __uint_as_float(w[k] << 16); g[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u); }
+  }
+}
+__device__ __forceinline__ void prefetch_gx16(const FclBiLstmBf16Params& p, long row, long prow, int col) {
+  const void* a = p.gx_blk ? static_cast<const void*>(p.gx_blk + ((size_t)(col >> 4) * (size_t)p.gx_rows + (size_t)prow) * 16)
+                           : static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(p.gx) + (size_t)row * (size_t)(8 * p.hidden) + col);
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+}
+
 struct BlShared {
   uint64_t full[4], empty[4];
   uint64_t tmem_full[2], tmem_empty[2];
@@ -118,9 +139,12 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     const int u = u_first + r;
     int off = 0, len = 0;
-    if (r < R && u < p.n_utts) { off = p.utt_off[u]; len = p.utt_off[u + 1] - off; }
+    long poff = 0;
+    if (r < R && u < p.n_utts) {
+      off = p.utt_off[u]; len = p.utt_off[u + 1] - off;
+      if (p.prow_off) poff = p.prow_off[u];
+    }
     float* cst = p.c_ws + ((size_t)(tile * 2 + dir) * H) * 128;        // [H][128]
-    const size_t gx_ld = (size_t)8 * H;                                // bf16 elements per gx row
     uint32_t chunk_ctr = 0;
 
     // zero the first h image (this thread's quarter of the k-chunks)
@@ -135,7 +159,11 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
       // stays in registers. The serial chain per step is 4x shorter than with one quarter doing all the work.
       const int uu = u_first + lane;
       int off2 = 0, len2 = 0;
-      if (uu < p.n_utts) { off2 = p.utt_off[uu]; len2 = p.utt_off[uu + 1] - off2; }
+      long poff2 = 0;
+      if (uu < p.n_utts) {
+        off2 = p.utt_off[uu]; len2 = p.utt_off[uu + 1] - off2;
+        if (p.prow_off) poff2 = p.prow_off[uu];
+      }
       const int usub = (cs * 4 + q) * 4;                     // first unit within a 64-unit chunk
       float creg[4][4];
 #pragma unroll
@@ -144,36 +172,32 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
         for (int j = 0; j < 4; ++j) creg[c][j] = 0.f;
       for (int t = 0; t < steps; ++t) {
         const bool active = t < len2;
-        const int grow = off2 + (dir == 0 ? t : len2 - 1 - t);
+        const int tt = dir == 0 ? t : len2 - 1 - t;
+        const int grow = off2 + tt;
+        const long gprow = poff2 + tt;
         uint8_t* hnew = himg + (size_t)((t + 1) & 1) * himg_bytes;
-        const __nv_bfloat16* gxr = reinterpret_cast<const __nv_bfloat16*>(p.gx) + (size_t)grow * gx_ld + (size_t)dir * 4 * H;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c < nch) {
             const int ub = c * 64 + usub;
-            uint4 g0 = make_uint4(0u, 0u, 0u, 0u), g1 = g0;
+            const int col = dir * 4 * H + 4 * ub;              // gate-interleaved column of unit ub, gate i
+            float gq[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) gq[j] = 0.f;
             if (active) {
-              g0 = __ldg(reinterpret_cast<const uint4*>(gxr + 4 * ub));
-              g1 = __ldg(reinterpret_cast<const uint4*>(gxr + 4 * ub) + 1);
-              if (t + 1 < len2 && (usub & 15) == 0) {      // one lane group per 128-byte line pulls the next step's gx into L2
-                const __nv_bfloat16* nx = reinterpret_cast<const __nv_bfloat16*>(p.gx) +
-                                          (size_t)(grow + (dir == 0 ? 1 : -1)) * gx_ld + (size_t)dir * 4 * H + 4 * ub;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-              }
+              load_gx16(p, grow, gprow, col, gq);
+              if (t + 1 < len2 && (p.gx_blk || (usub & 15) == 0))   // pull the next step's gx into L2
+                prefetch_gx16(p, grow + (dir == 0 ? 1 : -1), gprow + (dir == 0 ? 1 : -1), col);
             }
             const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
             mbar_wait(&sh.tmem_full[buf], use & 1u);
             tc_fence_after();
             float v[16], hf[4];
             tmem_ld16(lane_addr + buf * 256u + (uint32_t)(usub * 4), v);
-            const uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t w0 = gw[2 * j], w1 = gw[2 * j + 1];
-              const float gi = __uint_as_float(w0 << 16), gf = __uint_as_float(w0 & 0xFFFF0000u);
-              const float gg = __uint_as_float(w1 << 16), go = __uint_as_float(w1 & 0xFFFF0000u);
-              const float ig = sigmoid_fast(v[4 * j] + gi), fg = sigmoid_fast(v[4 * j + 1] + gf);
-              const float cg = tanh_fast(v[4 * j + 2] + gg), og = sigmoid_fast(v[4 * j + 3] + go);
+              const float ig = sigmoid_fast(v[4 * j] + gq[4 * j]), fg = sigmoid_fast(v[4 * j + 1] + gq[4 * j + 1]);
+              const float cg = tanh_fast(v[4 * j + 2] + gq[4 * j + 2]), og = sigmoid_fast(v[4 * j + 3] + gq[4 * j + 3]);
               const float cn = fmaf(fg, creg[c][j], ig * cg);
               hf[j] = active ? og * tanh_fast(cn) : 0.f;
               if (active) creg[c][j] = cn;
@@ -195,23 +219,27 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
     } else
     for (int t = 0; t < steps; ++t) {
       const bool active = t < len;
-      const int grow = off + (dir == 0 ? t : len - 1 - t);
+      const int tt = dir == 0 ? t : len - 1 - t;
+      const int grow = off + tt;
+      const long gprow = poff + tt;
       uint8_t* hnew = himg + (size_t)((t + 1) & 1) * himg_bytes;
-      const __nv_bfloat16* gxr = reinterpret_cast<const __nv_bfloat16*>(p.gx) + (size_t)grow * gx_ld + (size_t)dir * 4 * H;
 #pragma unroll 1
       for (int c = 0; c < nch; ++c) {
         const int u0 = c * 64 + cs * 16;                   // first of this thread's 16 hidden units
+        const int col0 = dir * 4 * H + 4 * u0;
         // request the global operands before waiting for the accumulator
-        uint4 gxv[8];
+        float gxv[2][16];                                 // two-deep: group g+1 is requested while group g is computed
         float cold[16];
         if (active) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) gxv[j] = __ldg(reinterpret_cast<const uint4*>(gxr + 4 * u0) + j);
+          load_gx16(p, grow, gprow, col0, gxv[0]);
 #pragma unroll
           for (int j = 0; j < 16; ++j) cold[j] = t == 0 ? 0.f : __ldcg(cst + (size_t)(u0 + j) * 128 + r);
-          if (t + 1 < len) {                               // pull the next step's gx line into L2
-            const __nv_bfloat16* nx = reinterpret_cast<const __nv_bfloat16*>(p.gx) + (size_t)(grow + (dir == 0 ? 1 : -1)) * gx_ld + (size_t)dir * 4 * H + 4 * u0;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+          if (t + 1 < len) {                               // pull the next step's gx lines into L2
+            prefetch_gx16(p, grow + (dir == 0 ? 1 : -1), gprow + (dir == 0 ? 1 : -1), col0);
+            if (p.gx_blk) {
+#pragma unroll
+              for (int j = 1; j < 4; ++j) prefetch_gx16(p, grow, gprow + (dir == 0 ? 1 : -1), col0 + 16 * j);
+            }
           }
         }
         const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
@@ -222,15 +250,13 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {                      // 4 units (16 accumulator columns) at a time
           float v[16];
+          if (active && g + 1 < 4) load_gx16(p, grow, gprow, col0 + 16 * (g + 1), gxv[(g + 1) & 1]);
           tmem_ld16(lane_addr + buf * 256u + (uint32_t)(cs * 64 + g * 16), v);
           if (active) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int ul = g * 4 + j;
-              const uint4 gq = gxv[ul >> 1];               // 8 bf16 = 2 units x 4 gates
-              const uint32_t w0 = (ul & 1) ? gq.z : gq.x, w1 = (ul & 1) ? gq.w : gq.y;
-              const float gi = __uint_as_float(w0 << 16), gf = __uint_as_float(w0 & 0xFFFF0000u);
-              const float gg = __uint_as_float(w1 << 16), go = __uint_as_float(w1 & 0xFFFF0000u);
+              const float gi = gxv[g & 1][4 * j], gf = gxv[g & 1][4 * j + 1], gg = gxv[g & 1][4 * j + 2], go = gxv[g & 1][4 * j + 3];
               const float ig = sigmoid_fast(v[4 * j] + gi), fg = sigmoid_fast(v[4 * j + 1] + gf);
               const float cg = tanh_fast(v[4 * j + 2] + gg), og = sigmoid_fast(v[4 * j + 3] + go);
               const float cn = fmaf(fg, cold[ul], ig * cg);
@@ -268,7 +294,8 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
 
 extern "C" int fcl_bilstm_bf16(const FclBiLstmBf16Params* p, void* stream) {
   using namespace fcl;
-  FCL_REQUIRE(p && p->utt_off && p->gx && p->whh_packed && p->c_ws && p->out, "null pointer");
+  FCL_REQUIRE(p && p->utt_off && (p->gx || p->gx_blk) && p->whh_packed && p->c_ws && p->out, "null pointer");
+  FCL_REQUIRE(!p->gx_blk || (p->prow_off && p->gx_rows > 0), "gx_blk needs prow_off and gx_rows");
   FCL_REQUIRE(p->n_utts > 0, "empty batch");
   FCL_REQUIRE(p->hidden % 64 == 0 && p->hidden >= 64 && p->hidden <= 256, "hidden must be 64, 128, 192 or 256");
   const int stages = p->hidden <= 128 ? 4 : 3;

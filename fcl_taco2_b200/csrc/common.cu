@@ -51,6 +51,9 @@ extern "C" int fcl_struct_size(int which) {
     case 12: return (int)sizeof(FclDecoderScheduleParams);
     case 13: return (int)sizeof(FclConvStackTilesParams);
     case 14: return (int)sizeof(FclConvStackParams);
+    case 15: return (int)sizeof(FclPadRowsParams);
+    case 16: return (int)sizeof(FclRowsToImageParams);
+    case 17: return (int)sizeof(FclConvImgParams);
     default: return -1;
   }
 }

@@ -66,6 +66,8 @@ class Engine:
             self.wb = {k: (t.to(self.device), nt, ks) for k, (t, nt, ks) in _pack.pack_bf16(packed).items()
                        if bf16_gemms is None or k in bf16_gemms}
             self.bf16_decoder = bf16_decoder
+            # front end as image-to-image convolutions (csrc/conv_img_bf16.cu) when every GEMM runs in bf16
+            self.wi = {k: (t.to(self.device), nb) for k, (t, nb) in _pack.pack_img(packed).items()} if bf16_gemms is None else {}
             self.dec_stream = _pack.pack_decoder_stream(packed, hp).to(self.device)
             self.dec_stream_pair = _pack.pack_decoder_stream(packed, hp, pair=True).to(self.device)
             self.blstm_whh_bf16 = None
@@ -84,6 +86,7 @@ class Engine:
         self.force_group = 0             # decoder group size override (tests); 0 = choose from the tile count
         self.use_pair = None             # cta_group::2 decoder (CTA pairs): None = when every SM has a tile anyway; True / False force it
         self.skip_zero_durations = False # extension: phonemes with d = 0 produce no frames (the reference's inference asserts)
+        self.use_img_convs = bool(getattr(self, "wi", None))   # padded-row-space image convolutions for encoder + predictors
         self.use_encoder_stack = False   # measured: with 256 channels only a 2-stage weight ring fits beside the images
         self.stage_events = None      # when a list: (stage, start_event, stop_event) appended per stage (bench.py)
 
@@ -169,11 +172,57 @@ class Engine:
                                  head_w=dptr(head_w), head_b=head_b, head_out=dptr(head_out), dur_out=dptr(dur_out))
         self._call("fcl_layernorm_f32", p)
 
+    # ------------------------------------------------------------------ padded row space / image convolutions
+    def pad_rows(self, utt_off, n_utts, n_rows):
+        """Padded row space of the batch (include/fcl_taco2.h): -> dict(n_tiles, rows_alloc, prow_src, prow_off)."""
+        gap = _lib.PAD_GAP
+        n_tiles = (n_rows + gap * (n_utts - 1) + 127) // 128
+        prow_src = self._buf((n_tiles * 128,), torch.int32)
+        prow_off = self._buf((n_utts + 1,), torch.int32)
+        self._call("fcl_pad_rows", _lib.PadRowsParams(n_utts=n_utts, n_rows=n_rows, gap=gap, utt_off=dptr(utt_off),
+                                                      n_tiles=n_tiles, prow_src=dptr(prow_src), prow_off=dptr(prow_off)))
+        return {"n_tiles": n_tiles, "rows_alloc": n_tiles * 128 + 8, "prow_src": prow_src, "prow_off": prow_off}
+
+    def rows_to_image(self, src, ld, chans, pad, gather=None):
+        img = self._buf((chans // 8 * pad["rows_alloc"] * 8,), torch.bfloat16)
+        self._call("fcl_rows_to_image", _lib.RowsToImageParams(n_tiles=pad["n_tiles"], chans=chans, src=dptr(src), ld=ld,
+                                                               gather=dptr(gather), prow_src=dptr(pad["prow_src"]),
+                                                               img=dptr(img)))
+        return img
+
+    def conv_img(self, key, in_img, pad, cin, cout, taps, act, epi, bias=None, gamma=None, beta=None, head_w=None,
+                 head_b=0.0, head_out=None, dur_out=None):
+        """One image-to-image conv launch. -> the output image (EPI_IMAGE / EPI_LN_IMAGE), the blocked fp32 buffer
+        (EPI_BLOCKED_F32) or None (EPI_LN_HEAD: results are in head_out / dur_out)."""
+        wp, nb = self.wi[key]
+        out_img = out_blk = None
+        if epi in (_lib.EPI_IMAGE, _lib.EPI_LN_IMAGE):
+            out_img = self._buf((cout // 8 * pad["rows_alloc"] * 8,), torch.bfloat16)
+        elif epi == _lib.EPI_BLOCKED_F32:
+            out_blk = self._buf((cout // 16 * pad["n_tiles"] * 128 * 16,), torch.float32)
+        self._call("fcl_conv_img_bf16", _lib.ConvImgParams(
+            n_tiles=pad["n_tiles"], cin=cin, cout=cout, taps=taps, nb=nb, act=act, epi=epi, in_img=dptr(in_img),
+            w_packed=dptr(wp), bias=dptr(bias), prow_src=dptr(pad["prow_src"]), out_img=dptr(out_img), out_blk=dptr(out_blk),
+            gamma=dptr(gamma), beta=dptr(beta), head_w=dptr(head_w), head_b=head_b, head_out=dptr(head_out),
+            dur_out=dptr(dur_out), n_pairs=0))
+        return out_img if out_img is not None else out_blk
+
     # ------------------------------------------------------------------ stages
     def encoder(self, ids, utt_off, seg, n_utts, lens=None):
         hp, w = self.hp, self.w
         P, E = ids.shape[0], hp.eunits
         x = None
+        pad = seg[3] if len(seg) > 3 else None
+        if pad is not None:
+            # embedding -> image, three k5 convs image -> image, input projection -> blocked fp32, recurrence
+            x = self.rows_to_image(w["embed"], hp.embed_dim, hp.embed_dim, pad, gather=ids)
+            cin = hp.embed_dim
+            for l in range(3):
+                x = self.conv_img(f"enc_conv{l}", x, pad, cin, hp.econv_chans, 5, ACT_RELU, _lib.EPI_IMAGE,
+                                  bias=w[f"enc_conv{l}_b"])
+                cin = hp.econv_chans
+            gx = self.conv_img("blstm_wih", x, pad, hp.econv_chans, 4 * E, 1, ACT_NONE, _lib.EPI_BLOCKED_F32, bias=w["blstm_b"])
+            return self._bilstm_bf16(None, utt_off, n_utts, P, gx_blk=gx, pad=pad)
         if self.precision == "bf16" and self.use_encoder_stack and all(f"enc_conv{l}" in self.wb for l in range(3)):
             if lens is None:
                 lens = np.diff(utt_off.cpu().numpy().astype(np.int64))
@@ -200,24 +249,42 @@ class Engine:
             gx = self._buf((P, 4 * E), torch.bfloat16)
             self.conv_gemm(x, None, w["blstm_b"], P, hp.econv_chans, 4 * E, 1, ACT_NONE, key="blstm_wih", out=gx,
                            out_bf16=True)
-            tile_utts = 32 if n_utts <= 32 * self.n_slots // 2 else 64 if n_utts <= 64 * self.n_slots // 2 else 128
-            n_tiles = (n_utts + tile_utts - 1) // tile_utts
-            c_ws = self._buf((n_tiles * 2 * (E // 2) * 128,), torch.float32)
-            self._call("fcl_bilstm_bf16", _lib.BiLstmBf16Params(n_utts=n_utts, hidden=E // 2, tile_utts=tile_utts,
-                                                                utt_off=dptr(utt_off),
-                                                                gx=dptr(gx), whh_packed=dptr(self.blstm_whh_bf16),
-                                                                c_ws=dptr(c_ws), out=dptr(h)))
-            return h
+            return self._bilstm_bf16(gx, utt_off, n_utts, P, h=h)
         gx = self.conv_gemm(x, w["blstm_wih"], w["blstm_b"], P, hp.econv_chans, 4 * E, 1, ACT_NONE, key="blstm_wih")
         p = _lib.BiLstmParams(n_utts=n_utts, hidden=E // 2, utt_off=dptr(utt_off), gx=dptr(gx), whh=dptr(w["blstm_whh"]),
                               out=dptr(h), group=8 if n_utts >= 8 else 1)
         self._call("fcl_bilstm_f32", p)
         return h
 
+    def _bilstm_bf16(self, gx, utt_off, n_utts, P, h=None, gx_blk=None, pad=None):
+        E = self.hp.eunits
+        if h is None:
+            h = self._buf((P, E), torch.float32)
+        tile_utts = 32 if n_utts <= 32 * self.n_slots // 2 else 64 if n_utts <= 64 * self.n_slots // 2 else 128
+        n_tiles = (n_utts + tile_utts - 1) // tile_utts
+        c_ws = self._buf((n_tiles * 2 * (E // 2) * 128,), torch.float32)
+        self._call("fcl_bilstm_bf16", _lib.BiLstmBf16Params(
+            n_utts=n_utts, hidden=E // 2, tile_utts=tile_utts, utt_off=dptr(utt_off), gx=dptr(gx),
+            whh_packed=dptr(self.blstm_whh_bf16), c_ws=dptr(c_ws), out=dptr(h), gx_blk=dptr(gx_blk),
+            prow_off=dptr(pad["prow_off"]) if pad else None, gx_rows=pad["n_tiles"] * 128 if pad else 0))
+        return h
+
     def predictor(self, name, h, seg, want_dur=False):
         """variance_predictor.py:86-93 / espnet DurationPredictor. -> (head (P,), dur int32 (P,) or None)"""
         hp, w = self.hp, self.w
         P, C = h.shape[0], hp.predictor_chans
+        pad = seg[3] if len(seg) > 3 else None
+        if pad is not None:
+            if "h_img" not in pad:                   # shared by the duration / pitch / energy predictors of a pass
+                pad["h_img"] = self.rows_to_image(h, hp.eunits, hp.eunits, pad)
+            x = self.conv_img(f"{name}_conv0", pad["h_img"], pad, hp.eunits, C, 3, ACT_RELU, _lib.EPI_LN_IMAGE,
+                              bias=w[f"{name}_conv0_b"], gamma=w[f"{name}_ln0_g"], beta=w[f"{name}_ln0_b"])
+            head = self._buf((P,), torch.float32)
+            dur = self._buf((P,), torch.int32) if want_dur else None
+            self.conv_img(f"{name}_conv1", x, pad, C, C, 3, ACT_RELU, _lib.EPI_LN_HEAD, bias=w[f"{name}_conv1_b"],
+                          gamma=w[f"{name}_ln1_g"], beta=w[f"{name}_ln1_b"], head_w=w[f"{name}_head_w"],
+                          head_b=self.head_b[name], head_out=head, dur_out=dur)
+            return head, dur
         x = self.conv_gemm(h, w[f"{name}_conv0_w"], w[f"{name}_conv0_b"], P, hp.eunits, C, 3, ACT_RELU, seg=seg,
                            key=f"{name}_conv0")
         self.layernorm(x, w[f"{name}_ln0_g"], w[f"{name}_ln0_b"], y=x)
@@ -549,7 +616,10 @@ class Engine:
             else:
                 lr = length_regulation(d["dur"], F)
         with self.stage("encoder"):
-            seg = (d["seg_lo"], d["seg_hi"], self.conv_tiles(d["utt_off"], B, int(((lens + 127) // 128).sum())))
+            if self.precision == "bf16" and self.use_img_convs and self.blstm_whh_bf16 is not None:
+                seg = (d["seg_lo"], d["seg_hi"], None, self.pad_rows(d["utt_off"], B, P))
+            else:
+                seg = (d["seg_lo"], d["seg_hi"], self.conv_tiles(d["utt_off"], B, int(((lens + 127) // 128).sum())))
             h = self.encoder(d["ids"], d["utt_off"], seg, B, lens=lens)
         dlog = dur_pred = None
         with self.stage("predictors"):

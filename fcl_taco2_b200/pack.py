@@ -114,6 +114,44 @@ def pack_conv_bf16(w: torch.Tensor, ntile: int | None = None, kstage: int | None
     return x.to(torch.bfloat16).reshape(-1).contiguous(), ntile, kstage
 
 
+def choose_nb(cout: int) -> int:
+    """MMA N of the image convolutions (csrc/conv_img_bf16.cu): largest multiple of 64 <= 256 dividing cout."""
+    for nb in (256, 192, 128, 64):
+        if cout % nb == 0:
+            return nb
+    raise ValueError(f"cout={cout} must be a multiple of 64")
+
+
+def pack_conv_pair(w: torch.Tensor, nb: int | None = None):
+    """(taps, cin, cout) fp32 -> bf16 half-stage blocks [cout/nb][cin/64][taps][2 halves][8][nb/2][8] for the
+    cta_group::2 image convolutions: each CTA of a pair loads its half (nb/2 output columns x 64 k) of every weight
+    stage as one contiguous block, already in the UMMA K-major no-swizzle core-matrix order. -> (flat bf16, nb)"""
+    taps, cin, cout = w.shape
+    nb = nb or choose_nb(cout)
+    assert cin % 64 == 0 and cout % nb == 0 and nb % 64 == 0 and nb <= 256
+    x = w.reshape(taps, cin // 64, 8, 8, cout // nb, 2, nb // 2)                   # t, kc, k8, j, blk, half, n
+    x = x.permute(4, 1, 0, 5, 2, 6, 3).contiguous()                                 # blk, kc, t, half, k8, n, j
+    return x.to(torch.bfloat16).reshape(-1).contiguous(), nb
+
+
+IMG_KEYS = ["enc_conv0", "enc_conv1", "enc_conv2", "blstm_wih", "dur_conv0", "dur_conv1", "pitch_conv0", "pitch_conv1",
+            "energy_conv0", "energy_conv1"]
+
+
+def pack_img(packed_fp32: dict) -> dict:
+    """Pair-split bf16 weights of the front-end image convolutions, or {} when a shape does not fit the kernel."""
+    out = {}
+    try:
+        for key in IMG_KEYS:
+            w = packed_fp32[key if key == "blstm_wih" else key + "_w"]
+            if w.shape[1] % 64 or w.shape[1] > 512 or w.shape[2] % 64 or w.shape[2] > 2048:
+                return {}
+            out[key] = pack_conv_pair(w)
+    except (ValueError, AssertionError):
+        return {}
+    return out
+
+
 STACK_KSTAGE = 32
 
 GEMM_KEYS = ["enc_conv0", "enc_conv1", "enc_conv2", "blstm_wih", "dur_conv0", "dur_conv1", "pitch_conv0", "pitch_conv1",

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 15
+#define FCL_ABI_VERSION 16
 
 enum {
   FCL_OK = 0,
@@ -183,6 +183,64 @@ typedef struct {
 } FclConvStackParams;
 int fcl_conv_stack_bf16(const FclConvStackParams* p, void* stream);
 
+/* ---------------------------------------------------------------- image-to-image convolutions (tcgen05, cta_group::2, TMA)
+ * Front-end form of the same convolutions (encoder_sa.py:134-140 conv stack, the LSTM input projection of
+ * encoder_sa.py:143-146, variance_predictor.py:48-66,86-90 and the espnet DurationPredictor): activations travel
+ * between layers as bf16 UMMA operand images in a PADDED row space, so a layer's input window is one tensor-map TMA
+ * load per 64-channel stage (no fp32 round trip, no conversion pass) and tiles are dense:
+ *   padded row of phoneme j of utterance u:  prow = utt_off[u] + gap*u + j      (gap zero rows between utterances:
+ *   the zero halo of every k-tap conv; "zero halo per utterance", never pad-and-convolve -- SURVEY.md 3.4)
+ *   image[c/8][prow + 4][c%8] bf16, (n_tiles*128 + 8) rows per 8-channel slab; rows that are not phonemes are ZERO
+ *   (every producer writes them), so consumers need no per-utterance logic at all.
+ * A CTA PAIR (2-CTA cluster) computes two 128-row tiles with one M=256 tcgen05.mma stream; each CTA loads its own
+ * input window and HALF of every weight stage (tensor-map TMA with .cta_group::2 completion on the leader's mbarrier).
+ * The grid is persistent (pairs walk super-tiles), accumulators live in TMEM (double-buffered when <= 256 columns).
+ */
+typedef struct {
+  int32_t n_utts, n_rows, gap;   /* gap >= taps/2 of every conv that reads the images (2 for k <= 5)             */
+  const int32_t* utt_off;        /* (B+1) row offsets (processing order)                                          */
+  int32_t n_tiles;               /* ceil((n_rows + gap*(n_utts-1)) / 128), computed by the caller                 */
+  int32_t* prow_src;             /* out (n_tiles*128): original row of every padded row, -1 = gap / tail          */
+  int32_t* prow_off;             /* out (B+1): padded row of the first phoneme of every utterance                 */
+} FclPadRowsParams;
+int fcl_pad_rows(const FclPadRowsParams* p, void* stream);
+
+typedef struct {
+  int32_t n_tiles, chans;        /* chans % 8 == 0                                                                */
+  const float* src;              /* (rows, ld) fp32, or the embedding table when gather != NULL                   */
+  int32_t ld;
+  const int64_t* gather;         /* optional: source row = gather[original row] (torch.nn.Embedding ids)          */
+  const int32_t* prow_src;       /* (n_tiles*128) from fcl_pad_rows                                               */
+  void* img;                     /* out bf16 [chans/8][n_tiles*128 + 8][8]                                        */
+} FclRowsToImageParams;
+int fcl_rows_to_image(const FclRowsToImageParams* p, void* stream);
+
+enum {
+  FCL_EPI_IMAGE = 0,        /* act(conv + bias) -> bf16 image                                                      */
+  FCL_EPI_LN_IMAGE = 1,     /* LayerNorm_C(act(conv + bias)) * gamma + beta -> bf16 image (variance_predictor.py:52-64) */
+  FCL_EPI_LN_HEAD = 2,      /* ... -> dot(., head_w) + head_b -> head_out[original row] (+ duration rounding)      */
+  FCL_EPI_BLOCKED_F32 = 3   /* conv + bias -> fp32, column-blocked by PADDED row: out[c/16][n_tiles*128][c%16]     */
+};
+typedef struct {
+  int32_t n_tiles, cin, cout, taps;   /* cin % 64 == 0; taps in {1,3,5}                                           */
+  int32_t nb;                         /* MMA N: multiple of 64, <= 256, divides cout (pack.py: pack_conv_pair)     */
+  int32_t act, epi;                   /* FCL_ACT_*, FCL_EPI_*                                                      */
+  const void* in_img;                 /* bf16 [cin/8][n_tiles*128 + 8][8]                                          */
+  const void* w_packed;               /* bf16 [cout/nb][cin/64][taps][2 halves][8][nb/2][8]                        */
+  const float* bias;                  /* optional (cout)                                                           */
+  const int32_t* prow_src;            /* (n_tiles*128)                                                             */
+  void* out_img;                      /* FCL_EPI_IMAGE / LN_IMAGE: bf16 [cout/8][n_tiles*128 + 8][8]               */
+  float* out_blk;                     /* FCL_EPI_BLOCKED_F32                                                       */
+  const float* gamma;                 /* LN epilogues: (cout), eps 1e-12 (espnet LayerNorm); cout <= 512           */
+  const float* beta;
+  const float* head_w;                /* FCL_EPI_LN_HEAD: (cout)                                                   */
+  float head_b;
+  float* head_out;                    /* (n_rows) by ORIGINAL row                                                  */
+  int32_t* dur_out;                   /* optional: clamp(round_half_even(exp(head) - 1), 0, FCL_MAX_DURATION)      */
+  int32_t n_pairs;                    /* CTA pairs to launch; 0 = min(SMs / 2, ceil(n_tiles / 2))                  */
+} FclConvImgParams;
+int fcl_conv_img_bf16(const FclConvImgParams* p, void* stream);
+
 /* ---------------------------------------------------------------- LayerNorm (+ optional head)
  * y = LayerNorm_C(x) * gamma + beta, eps 1e-12 (espnet LayerNorm, variance_predictor.py:62).
  * If head_w != NULL: head[r] = dot(y[r], head_w) + head_b (Linear(C,1), variance_predictor.py:90)
@@ -248,10 +306,14 @@ int fcl_bilstm_f32(const FclBiLstmParams* p, void* stream);
 typedef struct {
   int32_t n_utts, hidden, tile_utts;
   const int32_t* utt_off;
-  const void* gx;
+  const void* gx;            /* bf16 rows (see above), or NULL when gx_blk is given                              */
   const void* whh_packed;
   float* c_ws;
   float* out;                /* (P, 2*hidden) fp32: [fwd | bwd] */
+  const float* gx_blk;       /* optional: fp32 input projection, column-blocked by PADDED row
+                                [8*hidden/16][gx_rows][16] (fcl_conv_img_bf16, FCL_EPI_BLOCKED_F32)               */
+  const int32_t* prow_off;   /* (B+1) padded row of each utterance's first phoneme (with gx_blk)                  */
+  int32_t gx_rows;           /* n_tiles*128 (with gx_blk)                                                         */
 } FclBiLstmBf16Params;
 int fcl_bilstm_bf16(const FclBiLstmBf16Params* p, void* stream);
 
