@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 16
+ABI_VERSION = 18
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -99,7 +99,8 @@ class DecoderBf16Params(C.Structure):
 
 class BiLstmBf16Params(C.Structure):
     _fields_ = [("n_utts", i32), ("hidden", i32), ("tile_utts", i32), ("utt_off", ptr), ("gx", ptr),
-                ("whh_packed", ptr), ("c_ws", ptr), ("out", ptr), ("gx_blk", ptr), ("prow_off", ptr), ("gx_rows", i32)]
+                ("whh_packed", ptr), ("c_ws", ptr), ("out", ptr), ("gx_blk", ptr), ("prow_off", ptr), ("gx_rows", i32),
+                ("gx_blk_half", i32)]
 
 
 class PadRowsParams(C.Structure):
@@ -115,7 +116,7 @@ class ConvImgParams(C.Structure):
     _fields_ = [("n_tiles", i32), ("cin", i32), ("cout", i32), ("taps", i32), ("nb", i32), ("act", i32), ("epi", i32),
                 ("in_img", ptr), ("w_packed", ptr), ("bias", ptr), ("prow_src", ptr), ("out_img", ptr), ("out_blk", ptr),
                 ("gamma", ptr), ("beta", ptr), ("head_w", ptr), ("head_b", f32), ("head_out", ptr), ("dur_out", ptr),
-                ("n_pairs", i32)]
+                ("n_pairs", i32), ("trace", ptr), ("trace_cap", i32)]
 
 
 class DecoderScheduleParams(C.Structure):
@@ -157,7 +158,7 @@ PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_last_error", "fcl_sm_count", "fcl_struc
                  "fcl_ipc_close", "fcl_copy_async", "fcl_wait_flags", "fcl_write_flags"]
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
-EPI_IMAGE, EPI_LN_IMAGE, EPI_LN_HEAD, EPI_BLOCKED_F32 = 0, 1, 2, 3
+EPI_IMAGE, EPI_LN_IMAGE, EPI_LN_HEAD, EPI_BLOCKED_F32, EPI_BLOCKED_F16 = 0, 1, 2, 3, 4
 PAD_GAP = 2            # zero rows between utterances in the padded row space (halo of the k <= 5 convolutions)
 MAX_DURATION = 1023
 

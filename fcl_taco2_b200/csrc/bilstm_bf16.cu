@@ -16,6 +16,7 @@
 // warps 4-19 = epilogue (TMEM lane quarter = warp % 4 -> utterance row; column quarter = (warp-4)/4 -> 16 units).
 #include "common.cuh"
 #include "umma.cuh"
+#include <cuda_fp16.h>
 
 namespace fcl {
 using namespace umma;
@@ -27,7 +28,13 @@ constexpr uint32_t kBlBBytes = 256u * 64u * 2u;          // one W_hh stage: 256 
 // 16 consecutive gate-interleaved columns (4 hidden units x i,f,g,o) of the input projection of one phoneme:
 // either bf16 rows (P, 8H) or the fp32 column-blocked image [8H/16][gx_rows][16] in the padded row space.
 __device__ __forceinline__ void load_gx16(const FclBiLstmBf16Params& p, long row, long prow, int col, float (&g)[16]) {
-  if (p.gx_blk) {
+  if (p.gx_blk && p.gx_blk_half) {
+    const uint4* s = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.gx_blk) + ((size_t)(col >> 4) * (size_t)p.gx_rows + (size_t)prow) * 16);
+    const uint4 a = __ldg(s), b = __ldg(s + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k])); g[2 * k] = f.x; g[2 * k + 1] = f.y; }
+  } else if (p.gx_blk) {
     const float4* s = reinterpret_cast<const float4*>(p.gx_blk + ((size_t)(col >> 4) * (size_t)p.gx_rows + (size_t)prow) * 16);
 #pragma unroll
     for (int k = 0; k < 4; ++k) { const float4 v = __ldg(s + k); g[4 * k] = v.x; g[4 * k + 1] = v.y; g[4 * k + 2] = v.z; g[4 * k + 3] = v.w; }
@@ -40,7 +47,8 @@ __device__ __forceinline__ void load_gx16(const FclBiLstmBf16Params& p, long row
   }
 }
 __device__ __forceinline__ void prefetch_gx16(const FclBiLstmBf16Params& p, long row, long prow, int col) {
-  const void* a = p.gx_blk ? static_cast<const void*>(p.gx_blk + ((size_t)(col >> 4) * (size_t)p.gx_rows + (size_t)prow) * 16)
+  const void* a = p.gx_blk ? (p.gx_blk_half ? static_cast<const void*>(reinterpret_cast<const __half*>(p.gx_blk) + ((size_t)(col >> 4) * (size_t)p.gx_rows + (size_t)prow) * 16)
+                                            : static_cast<const void*>(p.gx_blk + ((size_t)(col >> 4) * (size_t)p.gx_rows + (size_t)prow) * 16))
                            : static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(p.gx) + (size_t)row * (size_t)(8 * p.hidden) + col);
   asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
 }
@@ -236,7 +244,7 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
           for (int j = 0; j < 16; ++j) cold[j] = t == 0 ? 0.f : __ldcg(cst + (size_t)(u0 + j) * 128 + r);
           if (t + 1 < len) {                               // pull the next step's gx lines into L2
             prefetch_gx16(p, grow + (dir == 0 ? 1 : -1), gprow + (dir == 0 ? 1 : -1), col0);
-            if (p.gx_blk) {
+            if (p.gx_blk) {                                 // the four 16-column blocks of this thread are separate lines
 #pragma unroll
               for (int j = 1; j < 4; ++j) prefetch_gx16(p, grow, gprow + (dir == 0 ? 1 : -1), col0 + 16 * j);
             }

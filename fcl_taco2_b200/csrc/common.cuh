@@ -65,4 +65,21 @@ __host__ __device__ __forceinline__ uint32_t dropout_threshold16(float p) {
   return (uint32_t)t;
 }
 
+// same for a kernel chosen at run time among template instantiations: keyed by (function pointer, device)
+static inline int ensure_dyn_smem_fn(const void* kernel, size_t bytes, const char* what) {
+  struct Entry { const void* fn; int dev; int bytes; };
+  static Entry table[64] = {};
+  static int n = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) {
+    for (int i = 0; i < n; ++i)
+      if (table[i].fn == kernel && table[i].dev == dev && table[i].bytes >= (int)bytes) return FCL_OK;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess && n < 64) { table[n].fn = kernel; table[n].dev = dev; table[n].bytes = (int)bytes; ++n; }
+  }
+  if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return FCL_ECUDA; }
+  return FCL_OK;
+}
+
 }  // namespace fcl

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 namespace fcl {
 namespace ci {
@@ -97,23 +98,42 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-  return act == FCL_ACT_RELU ? fmaxf(x, 0.f) : act == FCL_ACT_TANH ? tanh_fast(x) : x;
+// optional timeline of CTA 0 (debug / profiling aid; p.trace == nullptr in production): {event id, clock64}.
+// ids: 100 + blk (MMA issuer: accumulator slot free), 200 + blk (all MMAs of the block issued), 300 + rg (epilogue:
+// slot ready), 310 + rg (pass 1 done), 320 (moments exchanged), 330 + rg (pass 2 / plain epilogue done)
+__device__ __forceinline__ void ci_trace(const FclConvImgParams& p, int id) {
+  if (p.trace && blockIdx.x == 0) {
+    const unsigned long long n = atomicAdd(reinterpret_cast<unsigned long long*>(p.trace), 1ull);
+    if (n < (unsigned long long)p.trace_cap) { p.trace[2 + 2 * n] = id; p.trace[3 + 2 * n] = clock64(); }
+  }
 }
 
+template <int ACT>
+__device__ __forceinline__ float act_t(float x) {
+  if constexpr (ACT == FCL_ACT_RELU) return fmaxf(x, 0.f);
+  else if constexpr (ACT == FCL_ACT_TANH) return tanh_fast(x);
+  else return x;
+}
+
+template <int EPI, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap, FclConvImgParams p,
                 int a_stages, int b_stages, int n_pairs) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Shared sh;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) ci_trace(p, 1);                         // kernel entry
   const uint32_t rank = cluster_ctarank();
   const int pair = (int)blockIdx.x >> 1;
   const int taps = p.taps, halo = taps >> 1, nb = p.nb;
   const int kchunks = p.cin / 64, nblk = p.cout / nb;
-  const bool whole_row = p.epi == FCL_EPI_LN_IMAGE || p.epi == FCL_EPI_LN_HEAD;     // one accumulator = the whole output row
+  constexpr bool whole_row = EPI == FCL_EPI_LN_IMAGE || EPI == FCL_EPI_LN_HEAD;      // one accumulator = the whole output row
   const int acc_cols = whole_row ? p.cout : nb;
   const int n_bufs = acc_cols <= 256 ? 2 : 1;
+  // whole rows wider than 256 columns (predictors: 384 = 2 N blocks): the two N blocks are separate accumulator SLOTS
+  // with their own full/empty barriers, so the epilogue's first pass over block 0 overlaps the MMAs of block 1 and the
+  // next tile's block 0 starts as soon as block 0 has been normalised.
+  const bool split = whole_row && n_bufs == 1;
   const uint32_t b_bytes = (uint32_t)(nb / 2) * 128u;        // this CTA's half of a weight stage: nb/2 columns x 64 k
   const int n_super = (p.n_tiles + 1) >> 1;
   const long rows_alloc = (long)p.n_tiles * 128 + 8;
@@ -142,6 +162,7 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = sh.tmem_base;
+  if (tid == 0) ci_trace(p, 2);                         // set-up done
 
   if (warp == 0) {
     // ================================================================ TMA producer (both CTAs)
@@ -180,12 +201,14 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
       for (int st = pair; st < n_super; st += n_pairs) {
         const uint32_t a_base = a_ctr;
         for (int blk = 0; blk < nblk; ++blk) {
-          const uint32_t buf = acc_ctr % (uint32_t)n_bufs, use = acc_ctr / (uint32_t)n_bufs;
-          if (blk == 0 || !whole_row) {
+          const uint32_t buf = split ? (uint32_t)blk : acc_ctr % (uint32_t)n_bufs;
+          const uint32_t use = split ? acc_ctr : acc_ctr / (uint32_t)n_bufs;
+          if (blk == 0 || !whole_row || split) {
             mbar_wait(&sh.tmem_empty[buf], (use & 1u) ^ 1u);
             tc_fence_after();
+            ci_trace(p, 100 + blk);
           }
-          const uint32_t d_tmem = tmem + buf * 256u + (whole_row ? (uint32_t)(blk * nb) : 0u);
+          const uint32_t d_tmem = split ? tmem + (uint32_t)(blk * nb) : tmem + buf * 256u + (whole_row ? (uint32_t)(blk * nb) : 0u);
           for (int kc = 0; kc < kchunks; ++kc) {
             const uint32_t sa = (a_base + (uint32_t)kc) % (uint32_t)a_stages;
             if (blk == 0) {
@@ -209,9 +232,10 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
             }
             if (blk == nblk - 1) mma2_commit(&sh.a_empty[sa]);     // the window stage is free once the last N block used it
           }
-          if (blk == nblk - 1 || !whole_row) {
-            mma2_commit(&sh.tmem_full[buf]);            // accumulator ready in BOTH CTAs
-            ++acc_ctr;
+          if (blk == nblk - 1 || !whole_row || split) {
+            mma2_commit(&sh.tmem_full[buf]);            // accumulator (slot) ready in BOTH CTAs
+            ci_trace(p, 200 + blk);
+            if (!split || blk == nblk - 1) ++acc_ctr;
           }
         }
         a_ctr += (uint32_t)kchunks;
@@ -220,6 +244,9 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     __syncwarp();
   } else if (warp >= 4) {
     // ================================================================ epilogue (512 threads of each CTA, own 128 rows)
+    // Instruction-lean on purpose: with 16 warps the SM's four schedulers issue ~4 k warp-instructions per tile here,
+    // and in the LayerNorm variants part of that sits on the tile's critical path (the epilogue kind and the
+    // activation are template parameters, parameters come from shared memory as float4, addresses are incremental).
     const int q = warp & 3, cs = (warp - 4) >> 2;
     const int r = q * 32 + lane;                        // row within the tile == TMEM lane
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
@@ -227,135 +254,189 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     const uint32_t empty_leader = mapa_u32(&sh.tmem_empty[0], 0);
     uint32_t acc_ctr = 0, tile_ctr = 0;
     uint8_t* oimg = reinterpret_cast<uint8_t*>(p.out_img);
+    const size_t slab_stride = (size_t)rows_alloc * 16;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    auto release = [&](uint32_t slot) {                 // this warp has drained accumulator slot `slot`
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&sh.tmem_empty[slot]);
+        else mbar_arrive_cluster(empty_leader + slot * (uint32_t)sizeof(uint64_t));
+      }
+    };
     for (int st = pair; st < n_super; st += n_pairs, ++tile_ctr) {
       const int tile = 2 * st + (int)rank;
       const bool tile_ok = tile < p.n_tiles;
       const long prow = (long)tile * 128 + r;
       const int src = tile_ok ? __ldg(p.prow_src + prow) : -1;          // original row, -1 = gap row
-      const long srow = prow + kRowOff;                                 // stored image row
+      const bool live = src >= 0;
+      uint8_t* orow = oimg + (size_t)(prow + kRowOff) * 16;             // this row's 16-byte line in slab 0
       // guard rows of the output image that no tile owns: stored rows [0, 4) and [128 T + 4, 128 T + 8)
       long zrow = -1;
       if (tile == 0 && r < kRowOff) zrow = r;
       else if (tile == p.n_tiles - 1 && r >= 128 - kRowOff) zrow = (long)p.n_tiles * 128 + kRowOff + (r - (128 - kRowOff));
-      const int n_acc = whole_row ? 1 : nblk;
-      for (int a = 0; a < n_acc; ++a) {
-        const uint32_t buf = acc_ctr % (uint32_t)n_bufs, use = acc_ctr / (uint32_t)n_bufs;
-        const int c_base = (whole_row ? 0 : a * nb) + cs * cq;          // first output channel of this thread
-        const uint32_t t_addr = lane_addr + buf * 256u + (uint32_t)(cs * cq);
-        mbar_wait(&sh.tmem_full[buf], use & 1u);
-        tc_fence_after();
-        if (p.epi == FCL_EPI_IMAGE) {
+      if constexpr (EPI == FCL_EPI_IMAGE || EPI == FCL_EPI_BLOCKED_F32 || EPI == FCL_EPI_BLOCKED_F16) {
+        const int n_acc = whole_row ? 1 : nblk;
+        for (int a = 0; a < n_acc; ++a) {
+          const uint32_t buf = acc_ctr % (uint32_t)n_bufs, use = acc_ctr / (uint32_t)n_bufs;
+          const int c_base = a * nb + cs * cq;                          // first output channel of this thread
+          const uint32_t t_addr = lane_addr + buf * 256u + (uint32_t)(cs * cq);
+          mbar_wait(&sh.tmem_full[buf], use & 1u);
+          tc_fence_after();
+          if (tid == 128) ci_trace(p, 300 + a);
+#pragma unroll 1
           for (int g = 0; g < cq / 16; ++g) {
             float v[16];
             tmem_ld16(t_addr + (uint32_t)(g * 16), v);
             const int c0 = c_base + g * 16;
 #pragma unroll
-            for (int k8 = 0; k8 < 2; ++k8) {
-              float x[8];
+            for (int qd = 0; qd < 4; ++qd) {
+              const float4 b = *reinterpret_cast<const float4*>(sh.bias + c0 + 4 * qd);
+              v[4 * qd] = act_t<ACT>(v[4 * qd] + b.x); v[4 * qd + 1] = act_t<ACT>(v[4 * qd + 1] + b.y);
+              v[4 * qd + 2] = act_t<ACT>(v[4 * qd + 2] + b.z); v[4 * qd + 3] = act_t<ACT>(v[4 * qd + 3] + b.w);
+            }
+            if constexpr (EPI == FCL_EPI_IMAGE) {
+              uint4 w0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+              uint4 w1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+              if (!live) { w0 = zero4; w1 = zero4; }
+              if (tile_ok) {
+                uint8_t* o = orow + (size_t)(c0 >> 3) * slab_stride;
+                *reinterpret_cast<uint4*>(o) = w0;
+                *reinterpret_cast<uint4*>(o + slab_stride) = w1;
+              }
+            } else if constexpr (EPI == FCL_EPI_BLOCKED_F32) {
+              if (live) {
+                float4* o = reinterpret_cast<float4*>(p.out_blk + ((size_t)(c0 >> 4) * (size_t)p.n_tiles * 128 + (size_t)prow) * 16);
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                x[j] = src >= 0 ? apply_act(v[8 * k8 + j] + sh.bias[c0 + 8 * k8 + j], p.act) : 0.f;
-              const uint4 w = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
-              uint8_t* slab = oimg + (size_t)((c0 >> 3) + k8) * (size_t)rows_alloc * 16;
-              if (tile_ok) *reinterpret_cast<uint4*>(slab + (size_t)srow * 16) = w;
-              if (zrow >= 0) *reinterpret_cast<uint4*>(slab + (size_t)zrow * 16) = make_uint4(0u, 0u, 0u, 0u);
+                for (int qd = 0; qd < 4; ++qd) o[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+              }
+            } else {
+              if (live) {
+                uint32_t h[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const __half2 hh = __floats2half2_rn(fminf(fmaxf(v[2 * k], -65504.f), 65504.f), fminf(fmaxf(v[2 * k + 1], -65504.f), 65504.f));
+                  h[k] = *reinterpret_cast<const uint32_t*>(&hh);
+                }
+                uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_blk) + ((size_t)(c0 >> 4) * (size_t)p.n_tiles * 128 + (size_t)prow) * 16);
+                o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+              }
             }
           }
-        } else if (p.epi == FCL_EPI_BLOCKED_F32) {
-          for (int g = 0; g < cq / 16; ++g) {
+          release(buf);
+          if (tid == 128) ci_trace(p, 330 + a);
+          ++acc_ctr;
+          if (EPI == FCL_EPI_IMAGE && zrow >= 0)                        // rare: first / last tile only
+            for (int k8 = 0; k8 < cq / 8; ++k8) *reinterpret_cast<uint4*>(oimg + (size_t)((c_base >> 3) + k8) * slab_stride + (size_t)zrow * 16) = zero4;
+        }
+      } else {
+        // ---- LayerNorm over the whole row: 4 threads per row, each owns `cr` columns of every range (one range, or one
+        // per N block in split mode). Pass 1 = moments; pass 2 = normalise, reading TMEM again (cheaper than holding the
+        // row in registers). In split mode pass 1 of block 0 runs under the MMAs of block 1, and block 0 is handed back
+        // to the MMA issuer before block 1 is normalised.
+        const uint32_t buf = split ? 0u : acc_ctr % (uint32_t)n_bufs;
+        const uint32_t use = split ? acc_ctr : acc_ctr / (uint32_t)n_bufs;
+        const uint32_t t_base = lane_addr + (split ? 0u : buf * 256u);
+        const int par = (int)(tile_ctr & 1u);
+        const int n_rng = split ? nblk : 1;
+        const int cr = split ? nb / 4 : cq;
+        float s1 = 0.f, s2 = 0.f;
+        for (int rg = 0; rg < n_rng; ++rg) {
+          mbar_wait(&sh.tmem_full[split ? (uint32_t)rg : buf], use & 1u);
+          tc_fence_after();
+          if (tid == 128) ci_trace(p, 300 + rg);
+          const int cb = (split ? rg * nb : 0) + cs * cr;
+#pragma unroll 1
+          for (int g = 0; g < cr / 16; ++g) {
             float v[16];
-            tmem_ld16(t_addr + (uint32_t)(g * 16), v);
-            const int c0 = c_base + g * 16;
-            if (src >= 0) {
-              float4* o = reinterpret_cast<float4*>(p.out_blk + ((size_t)(c0 >> 4) * (size_t)p.n_tiles * 128 + (size_t)prow) * 16);
+            tmem_ld16(t_base + (uint32_t)(cb + g * 16), v);
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+              const float4 b = *reinterpret_cast<const float4*>(sh.bias + cb + g * 16 + 4 * qd);
+              const float x0 = act_t<ACT>(v[4 * qd] + b.x), x1 = act_t<ACT>(v[4 * qd + 1] + b.y);
+              const float x2 = act_t<ACT>(v[4 * qd + 2] + b.z), x3 = act_t<ACT>(v[4 * qd + 3] + b.w);
+              s1 += (x0 + x1) + (x2 + x3);
+              s2 = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, s2))));
+            }
+          }
+          if (tid == 128) ci_trace(p, 310 + rg);
+        }
+        sh.ln_part[par][cs][r][0] = s1;
+        sh.ln_part[par][cs][r][1] = s2;
+        epi_bar_sync();
+        if (tid == 128) ci_trace(p, 320);
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { t1 += sh.ln_part[par][k][r][0]; t2 += sh.ln_part[par][k][r][1]; }
+        const float inv_c = 1.0f / (float)p.cout;
+        const float mean = t1 * inv_c;
+        const float var = fmaxf(t2 * inv_c - mean * mean, 0.f);          // biased variance (torch layer_norm)
+        const float rstd = 1.0f / sqrtf(var + 1e-12f);
+        const float nmr = -mean * rstd;                                  // (x - mean) * rstd = fma(x, rstd, nmr)
+        float dot = 0.f;
+        for (int rg = 0; rg < n_rng; ++rg) {
+          const int cb = (split ? rg * nb : 0) + cs * cr;
+#pragma unroll 1
+          for (int g = 0; g < cr / 16; ++g) {
+            float v[16];
+            tmem_ld16(t_base + (uint32_t)(cb + g * 16), v);
+            const int c0 = cb + g * 16;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+              const float4 b = *reinterpret_cast<const float4*>(sh.bias + c0 + 4 * qd);
+              const float4 ga = *reinterpret_cast<const float4*>(sh.gamma + c0 + 4 * qd);
+              const float4 be = *reinterpret_cast<const float4*>(sh.beta + c0 + 4 * qd);
+              v[4 * qd] = fmaf(fmaf(act_t<ACT>(v[4 * qd] + b.x), rstd, nmr), ga.x, be.x);
+              v[4 * qd + 1] = fmaf(fmaf(act_t<ACT>(v[4 * qd + 1] + b.y), rstd, nmr), ga.y, be.y);
+              v[4 * qd + 2] = fmaf(fmaf(act_t<ACT>(v[4 * qd + 2] + b.z), rstd, nmr), ga.z, be.z);
+              v[4 * qd + 3] = fmaf(fmaf(act_t<ACT>(v[4 * qd + 3] + b.w), rstd, nmr), ga.w, be.w);
+            }
+            if constexpr (EPI == FCL_EPI_LN_HEAD) {
 #pragma unroll
               for (int qd = 0; qd < 4; ++qd) {
-                const float4 b = *reinterpret_cast<const float4*>(sh.bias + c0 + 4 * qd);
-                o[qd] = make_float4(v[4 * qd] + b.x, v[4 * qd + 1] + b.y, v[4 * qd + 2] + b.z, v[4 * qd + 3] + b.w);
+                const float4 hw = *reinterpret_cast<const float4*>(sh.head_w + c0 + 4 * qd);
+                dot = fmaf(v[4 * qd], hw.x, fmaf(v[4 * qd + 1], hw.y, fmaf(v[4 * qd + 2], hw.z, fmaf(v[4 * qd + 3], hw.w, dot))));
               }
-            }
-          }
-        } else {
-          // ---- LayerNorm over the whole row (4 threads per row, one column quarter each): pass 1 = moments
-          const int par = (int)(tile_ctr & 1u);
-          float s1 = 0.f, s2 = 0.f;
-          for (int g = 0; g < cq / 16; ++g) {
-            float v[16];
-            tmem_ld16(t_addr + (uint32_t)(g * 16), v);
-            const int c0 = c_base + g * 16;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float x = apply_act(v[j] + sh.bias[c0 + j], p.act);
-              s1 += x;
-              s2 = fmaf(x, x, s2);
-            }
-          }
-          sh.ln_part[par][cs][r][0] = s1;
-          sh.ln_part[par][cs][r][1] = s2;
-          epi_bar_sync();
-          float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { t1 += sh.ln_part[par][k][r][0]; t2 += sh.ln_part[par][k][r][1]; }
-          const float inv_c = 1.0f / (float)p.cout;
-          const float mean = t1 * inv_c;
-          const float var = fmaxf(t2 * inv_c - mean * mean, 0.f);        // biased variance (torch layer_norm)
-          const float rstd = 1.0f / sqrtf(var + 1e-12f);
-          // ---- pass 2: normalise (TMEM is read again: cheaper than holding the row in registers)
-          float dot = 0.f;
-          for (int g = 0; g < cq / 16; ++g) {
-            float v[16];
-            tmem_ld16(t_addr + (uint32_t)(g * 16), v);
-            const int c0 = c_base + g * 16;
-            float y[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float x = apply_act(v[j] + sh.bias[c0 + j], p.act);
-              y[j] = (x - mean) * rstd * sh.gamma[c0 + j] + sh.beta[c0 + j];
-            }
-            if (p.epi == FCL_EPI_LN_HEAD) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) dot = fmaf(y[j], sh.head_w[c0 + j], dot);
             } else {
-#pragma unroll
-              for (int k8 = 0; k8 < 2; ++k8) {
-                uint4 w = make_uint4(0u, 0u, 0u, 0u);
-                if (src >= 0)
-                  w = make_uint4(pack_bf16(y[8 * k8], y[8 * k8 + 1]), pack_bf16(y[8 * k8 + 2], y[8 * k8 + 3]),
-                                 pack_bf16(y[8 * k8 + 4], y[8 * k8 + 5]), pack_bf16(y[8 * k8 + 6], y[8 * k8 + 7]));
-                uint8_t* slab = oimg + (size_t)((c0 >> 3) + k8) * (size_t)rows_alloc * 16;
-                if (tile_ok) *reinterpret_cast<uint4*>(slab + (size_t)srow * 16) = w;
-                if (zrow >= 0) *reinterpret_cast<uint4*>(slab + (size_t)zrow * 16) = make_uint4(0u, 0u, 0u, 0u);
+              uint4 w0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+              uint4 w1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+              if (!live) { w0 = zero4; w1 = zero4; }
+              if (tile_ok) {
+                uint8_t* o = orow + (size_t)(c0 >> 3) * slab_stride;
+                *reinterpret_cast<uint4*>(o) = w0;
+                *reinterpret_cast<uint4*>(o + slab_stride) = w1;
               }
             }
           }
-          if (p.epi == FCL_EPI_LN_HEAD) {
-            sh.head_part[par][cs][r] = dot;
-            epi_bar_sync();
-            if (cs == 0 && src >= 0) {
-              const float h = ((sh.head_part[par][0][r] + sh.head_part[par][1][r]) + (sh.head_part[par][2][r] + sh.head_part[par][3][r])) + p.head_b;
-              if (p.head_out) p.head_out[src] = h;
-              if (p.dur_out) {
-                // clamp(round_half_even(exp(x) - 1), 0, cap); rintf rounds half to even like torch.round
-                float d = rintf(expf(h) - 1.0f);
-                d = fminf(fmaxf(d, 0.f), (float)FCL_MAX_DURATION);
-                p.dur_out[src] = (int)d;
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (rank == 0) mbar_arrive(&sh.tmem_empty[buf]);
-          else mbar_arrive_cluster(empty_leader + buf * (uint32_t)sizeof(uint64_t));
+          release(split ? (uint32_t)rg : buf);             // block `rg` is drained: the next tile's MMAs may overwrite it
+          if (tid == 128) ci_trace(p, 330 + rg);
+          if (EPI == FCL_EPI_LN_IMAGE && zrow >= 0)
+            for (int k8 = 0; k8 < cr / 8; ++k8) *reinterpret_cast<uint4*>(oimg + (size_t)((cb >> 3) + k8) * slab_stride + (size_t)zrow * 16) = zero4;
         }
         ++acc_ctr;
+        if constexpr (EPI == FCL_EPI_LN_HEAD) {
+          sh.head_part[par][cs][r] = dot;
+          epi_bar_sync();
+          if (cs == 0 && live) {
+            const float h = ((sh.head_part[par][0][r] + sh.head_part[par][1][r]) + (sh.head_part[par][2][r] + sh.head_part[par][3][r])) + p.head_b;
+            if (p.head_out) p.head_out[src] = h;
+            if (p.dur_out) {
+              // clamp(round_half_even(exp(x) - 1), 0, cap); rintf rounds half to even like torch.round
+              float d = rintf(expf(h) - 1.0f);
+              d = fminf(fmaxf(d, 0.f), (float)FCL_MAX_DURATION);
+              p.dur_out[src] = (int)d;
+            }
+          }
+        }
       }
     }
   }
   tc_fence_before();
+  if (tid == 0) ci_trace(p, 3);                         // producer done
   cluster_sync_all();                                   // the leader's MMAs read the peer's shared memory: leave together
   if (warp == 2) tmem_dealloc2(tmem, 512);
+  if (tid == 0) ci_trace(p, 4);                         // exit
 }
 
 // ---------------------------------------------------------------- padded row space
@@ -452,11 +533,12 @@ extern "C" int fcl_conv_img_bf16(const FclConvImgParams* p, void* stream) {
   FCL_REQUIRE(p->nb >= 64 && p->nb <= 256 && p->nb % 64 == 0 && p->cout % p->nb == 0, "nb must be a multiple of 64 (<= 256) dividing cout");
   FCL_REQUIRE(p->cout <= 2048, "cout must be <= 2048");
   const bool ln = p->epi == FCL_EPI_LN_IMAGE || p->epi == FCL_EPI_LN_HEAD;
-  FCL_REQUIRE(p->epi >= FCL_EPI_IMAGE && p->epi <= FCL_EPI_BLOCKED_F32, "unknown epilogue");
+  FCL_REQUIRE(p->epi >= FCL_EPI_IMAGE && p->epi <= FCL_EPI_BLOCKED_F16, "unknown epilogue");
   FCL_REQUIRE(!ln || (p->cout <= 512 && p->gamma && p->beta), "LayerNorm epilogues need gamma/beta and cout <= 512");
+  FCL_REQUIRE(!ln || p->cout <= 256 || p->cout == 2 * p->nb, "LayerNorm rows wider than 256 columns must be exactly two N blocks");
   FCL_REQUIRE(p->epi != FCL_EPI_LN_HEAD || (p->head_w && (p->head_out || p->dur_out)), "head epilogue needs head_w and an output");
   FCL_REQUIRE((p->epi != FCL_EPI_IMAGE && p->epi != FCL_EPI_LN_IMAGE) || p->out_img, "image epilogues need out_img");
-  FCL_REQUIRE(p->epi != FCL_EPI_BLOCKED_F32 || p->out_blk, "blocked epilogue needs out_blk");
+  FCL_REQUIRE((p->epi != FCL_EPI_BLOCKED_F32 && p->epi != FCL_EPI_BLOCKED_F16) || p->out_blk, "blocked epilogues need out_blk");
   EncodeTiledFn enc = encode_fn();
   if (!enc) { set_error("fcl_conv_img_bf16: cuTensorMapEncodeTiled is not available from this driver"); return FCL_EUNSUPPORTED; }
   const int kchunks = p->cin / 64, nblk = p->cout / p->nb;
@@ -493,7 +575,16 @@ extern "C" int fcl_conv_img_bf16(const FclConvImgParams* p, void* stream) {
   if (b_stages > kMaxStages) b_stages = kMaxStages;
   FCL_REQUIRE(b_stages >= 2, "shared memory budget exceeded");
   const size_t smem = (size_t)a_stages * kABytes + (size_t)b_stages * b_bytes + 1024;      // + alignment slack
-  if (int rc = ensure_dyn_smem(conv_img_kernel, smem, "fcl_conv_img_bf16")) return rc;
+  typedef void (*Kern)(const CUtensorMap, const CUtensorMap, FclConvImgParams, int, int, int);
+  Kern kern = nullptr;
+  const int act = p->act;
+  if (p->epi == FCL_EPI_IMAGE) kern = act == FCL_ACT_RELU ? conv_img_kernel<FCL_EPI_IMAGE, FCL_ACT_RELU> : act == FCL_ACT_TANH ? conv_img_kernel<FCL_EPI_IMAGE, FCL_ACT_TANH> : conv_img_kernel<FCL_EPI_IMAGE, FCL_ACT_NONE>;
+  else if (p->epi == FCL_EPI_LN_IMAGE) kern = act == FCL_ACT_RELU ? conv_img_kernel<FCL_EPI_LN_IMAGE, FCL_ACT_RELU> : conv_img_kernel<FCL_EPI_LN_IMAGE, FCL_ACT_NONE>;
+  else if (p->epi == FCL_EPI_LN_HEAD) kern = act == FCL_ACT_RELU ? conv_img_kernel<FCL_EPI_LN_HEAD, FCL_ACT_RELU> : conv_img_kernel<FCL_EPI_LN_HEAD, FCL_ACT_NONE>;
+  else if (p->epi == FCL_EPI_BLOCKED_F32) kern = act == FCL_ACT_RELU ? conv_img_kernel<FCL_EPI_BLOCKED_F32, FCL_ACT_RELU> : conv_img_kernel<FCL_EPI_BLOCKED_F32, FCL_ACT_NONE>;
+  else kern = act == FCL_ACT_RELU ? conv_img_kernel<FCL_EPI_BLOCKED_F16, FCL_ACT_RELU> : conv_img_kernel<FCL_EPI_BLOCKED_F16, FCL_ACT_NONE>;
+  FCL_REQUIRE(act == FCL_ACT_NONE || act == FCL_ACT_RELU || (act == FCL_ACT_TANH && p->epi == FCL_EPI_IMAGE), "unsupported activation for this epilogue");
+  if (int rc = ensure_dyn_smem_fn(reinterpret_cast<const void*>(kern), smem, "fcl_conv_img_bf16")) return rc;
   int sms = fcl_sm_count();
   if (sms < 0) return sms;
   const int n_super = (p->n_tiles + 1) / 2;
@@ -510,7 +601,7 @@ extern "C" int fcl_conv_img_bf16(const FclConvImgParams* p, void* stream) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_img_kernel, amap, wmap, *p, a_stages, b_stages, n_pairs);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, amap, wmap, *p, a_stages, b_stages, n_pairs);
   if (e != cudaSuccess) { set_error("fcl_conv_img_bf16: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
   return check_launch("fcl_conv_img_bf16");
 }

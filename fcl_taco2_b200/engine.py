@@ -22,7 +22,7 @@ from .hparams import HParams
 from .plan import output_chunks, BatchPlan
 
 
-_ELEM_SIZE = {torch.float32: 4, torch.int32: 4, torch.bfloat16: 2, torch.int64: 8, torch.uint8: 1}
+_ELEM_SIZE = {torch.float32: 4, torch.int32: 4, torch.bfloat16: 2, torch.float16: 2, torch.int64: 8, torch.uint8: 1}
 
 
 @dataclass
@@ -200,6 +200,8 @@ class Engine:
             out_img = self._buf((cout // 8 * pad["rows_alloc"] * 8,), torch.bfloat16)
         elif epi == _lib.EPI_BLOCKED_F32:
             out_blk = self._buf((cout // 16 * pad["n_tiles"] * 128 * 16,), torch.float32)
+        elif epi == _lib.EPI_BLOCKED_F16:
+            out_blk = self._buf((cout // 16 * pad["n_tiles"] * 128 * 16,), torch.float16)
         self._call("fcl_conv_img_bf16", _lib.ConvImgParams(
             n_tiles=pad["n_tiles"], cin=cin, cout=cout, taps=taps, nb=nb, act=act, epi=epi, in_img=dptr(in_img),
             w_packed=dptr(wp), bias=dptr(bias), prow_src=dptr(pad["prow_src"]), out_img=dptr(out_img), out_blk=dptr(out_blk),
@@ -221,7 +223,9 @@ class Engine:
                 x = self.conv_img(f"enc_conv{l}", x, pad, cin, hp.econv_chans, 5, ACT_RELU, _lib.EPI_IMAGE,
                                   bias=w[f"enc_conv{l}_b"])
                 cin = hp.econv_chans
-            gx = self.conv_img("blstm_wih", x, pad, hp.econv_chans, 4 * E, 1, ACT_NONE, _lib.EPI_BLOCKED_F32, bias=w["blstm_b"])
+            # gate pre-activations in fp16 (11-bit significand, |x| << 65504): half the HBM bytes of fp32, and the
+            # write-back of this launch is what bounds it; bf16 here was the largest single rounding of the encoder
+            gx = self.conv_img("blstm_wih", x, pad, hp.econv_chans, 4 * E, 1, ACT_NONE, _lib.EPI_BLOCKED_F16, bias=w["blstm_b"])
             return self._bilstm_bf16(None, utt_off, n_utts, P, gx_blk=gx, pad=pad)
         if self.precision == "bf16" and self.use_encoder_stack and all(f"enc_conv{l}" in self.wb for l in range(3)):
             if lens is None:
@@ -266,7 +270,8 @@ class Engine:
         self._call("fcl_bilstm_bf16", _lib.BiLstmBf16Params(
             n_utts=n_utts, hidden=E // 2, tile_utts=tile_utts, utt_off=dptr(utt_off), gx=dptr(gx),
             whh_packed=dptr(self.blstm_whh_bf16), c_ws=dptr(c_ws), out=dptr(h), gx_blk=dptr(gx_blk),
-            prow_off=dptr(pad["prow_off"]) if pad else None, gx_rows=pad["n_tiles"] * 128 if pad else 0))
+            prow_off=dptr(pad["prow_off"]) if pad else None, gx_rows=pad["n_tiles"] * 128 if pad else 0,
+            gx_blk_half=1 if (gx_blk is not None and gx_blk.dtype == torch.float16) else 0))
         return h
 
     def predictor(self, name, h, seg, want_dur=False):

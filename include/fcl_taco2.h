@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 16
+#define FCL_ABI_VERSION 18
 
 enum {
   FCL_OK = 0,
@@ -219,7 +219,8 @@ enum {
   FCL_EPI_IMAGE = 0,        /* act(conv + bias) -> bf16 image                                                      */
   FCL_EPI_LN_IMAGE = 1,     /* LayerNorm_C(act(conv + bias)) * gamma + beta -> bf16 image (variance_predictor.py:52-64) */
   FCL_EPI_LN_HEAD = 2,      /* ... -> dot(., head_w) + head_b -> head_out[original row] (+ duration rounding)      */
-  FCL_EPI_BLOCKED_F32 = 3   /* conv + bias -> fp32, column-blocked by PADDED row: out[c/16][n_tiles*128][c%16]     */
+  FCL_EPI_BLOCKED_F32 = 3,  /* conv + bias -> fp32, column-blocked by PADDED row: out[c/16][n_tiles*128][c%16]     */
+  FCL_EPI_BLOCKED_F16 = 4   /* same layout in fp16 (saturating): half the HBM bytes, 11-bit significand            */
 };
 typedef struct {
   int32_t n_tiles, cin, cout, taps;   /* cin % 64 == 0; taps in {1,3,5}                                           */
@@ -230,7 +231,7 @@ typedef struct {
   const float* bias;                  /* optional (cout)                                                           */
   const int32_t* prow_src;            /* (n_tiles*128)                                                             */
   void* out_img;                      /* FCL_EPI_IMAGE / LN_IMAGE: bf16 [cout/8][n_tiles*128 + 8][8]               */
-  float* out_blk;                     /* FCL_EPI_BLOCKED_F32                                                       */
+  float* out_blk;                     /* FCL_EPI_BLOCKED_F32 (float) / FCL_EPI_BLOCKED_F16 (__half)                */
   const float* gamma;                 /* LN epilogues: (cout), eps 1e-12 (espnet LayerNorm); cout <= 512           */
   const float* beta;
   const float* head_w;                /* FCL_EPI_LN_HEAD: (cout)                                                   */
@@ -238,6 +239,8 @@ typedef struct {
   float* head_out;                    /* (n_rows) by ORIGINAL row                                                  */
   int32_t* dur_out;                   /* optional: clamp(round_half_even(exp(head) - 1), 0, FCL_MAX_DURATION)      */
   int32_t n_pairs;                    /* CTA pairs to launch; 0 = min(SMs / 2, ceil(n_tiles / 2))                  */
+  int64_t* trace;                     /* optional debug timeline of CTA 0: [0] = count (zero it), then (id, clock) pairs */
+  int32_t trace_cap;                  /* capacity in records                                                        */
 } FclConvImgParams;
 int fcl_conv_img_bf16(const FclConvImgParams* p, void* stream);
 
@@ -314,6 +317,7 @@ typedef struct {
                                 [8*hidden/16][gx_rows][16] (fcl_conv_img_bf16, FCL_EPI_BLOCKED_F32)               */
   const int32_t* prow_off;   /* (B+1) padded row of each utterance's first phoneme (with gx_blk)                  */
   int32_t gx_rows;           /* n_tiles*128 (with gx_blk)                                                         */
+  int32_t gx_blk_half;       /* != 0: gx_blk holds fp16 (FCL_EPI_BLOCKED_F16) instead of fp32                    */
 } FclBiLstmBf16Params;
 int fcl_bilstm_bf16(const FclBiLstmBf16Params* p, void* stream);
 

@@ -160,8 +160,9 @@ def test_conv_img_layernorm_epilogues(total, cin, C, head):
         assert float((rows[valid] - y).abs().max()) < 1e-2 * max(1.0, float(y.abs().max()))
 
 
+@pytest.mark.parametrize("half", [False, True])
 @pytest.mark.parametrize("total,cin,cout", [(900, 256, 1024), (200 * 128, 256, 1024), (600, 512, 2048)])
-def test_conv_img_blocked_f32_epilogue(total, cin, cout):
+def test_conv_img_blocked_epilogues(total, cin, cout, half):
     """The BiLSTM input projection: linear + bias -> fp32, column-blocked [cout/16][n_tiles*128][16] by padded row."""
     rs = np.random.RandomState(total + cout)
     g = torch.Generator().manual_seed(total)
@@ -174,14 +175,14 @@ def test_conv_img_blocked_f32_epilogue(total, cin, cout):
     wp, bias_d = wp.cuda(), bias.cuda()
     img = _to_image(a, pd)
     R = pd["n_tiles"] * 128
-    out = torch.full((cout // 16 * R * 16,), float("nan"), device="cuda")
+    out = torch.full((cout // 16 * R * 16,), float("nan"), device="cuda", dtype=torch.float16 if half else torch.float32)
     _lib.call("fcl_conv_img_bf16", _lib.ConvImgParams(n_tiles=pd["n_tiles"], cin=cin, cout=cout, taps=1, nb=nb, act=_lib.ACT_NONE,
-                                                      epi=_lib.EPI_BLOCKED_F32, in_img=dptr(img), w_packed=dptr(wp), bias=dptr(bias_d),
+                                                      epi=_lib.EPI_BLOCKED_F16 if half else _lib.EPI_BLOCKED_F32, in_img=dptr(img), w_packed=dptr(wp), bias=dptr(bias_d),
                                                       prow_src=dptr(pd["prow_src"]), out_blk=dptr(out)), _stream())
     torch.cuda.synchronize()
-    rows = out.view(cout // 16, R, 16).permute(1, 0, 2).reshape(R, cout).cpu()
+    rows = out.float().view(cout // 16, R, 16).permute(1, 0, 2).reshape(R, cout).cpu()
     valid = (pd["prow_src"].cpu() >= 0)
     ref = a.to(torch.bfloat16).float() @ w[0].to(torch.bfloat16).float() + bias
     got = rows[valid]
     assert torch.isfinite(got).all()
-    assert float((got - ref).abs().max()) < 2e-3 * max(1.0, float(ref.abs().max()))
+    assert float((got - ref).abs().max()) < (3e-3 if half else 2e-3) * max(1.0, float(ref.abs().max()))

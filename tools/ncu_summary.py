@@ -22,10 +22,13 @@ def main(path, title):
         for k in KEYS:
             if k in d:
                 print(f"| {k} | {d[k][1]} | {d[k][0]} |")
-        stalls = sorted(((float(v[1] or 0), h) for h, v in d.items()
-                         if "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct")), reverse=True)[:5]
-        print("\ntop warp-stall reasons (% of warp-active): " +
-              ", ".join(f"{h.split('issue_stalled_')[1].replace('_per_warp_active.pct', '')} {v:.0f}" for v, h in stalls) + "\n")
+        # warp-state sampling (pcsamp): share of the samples per stall reason
+        samp = {h.split("issue_stalled_")[1]: float((v[1] or "0").replace(",", "")) for h, v in d.items()
+                if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued")}
+        tot = sum(samp.values()) or 1.0
+        top = sorted(samp.items(), key=lambda kv: -kv[1])[:6]
+        print("\ntop warp-stall reasons (% of sampled warp states): " +
+              ", ".join(f"{k} {100 * v / tot:.0f}" for k, v in top) + "\n")
 
 
 if __name__ == "__main__":
