@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -94,7 +94,7 @@ class DecoderBf16Params(C.Structure):
                 ("wpos", ptr), ("b0", ptr), ("b1", ptr), ("group", i32), ("act_priv", ptr), ("act_shared", ptr),
                 ("c_ws", ptr), ("group_sync", ptr), ("before", ptr),
                 ("zoneout", f32), ("dropout_p", f32), ("dropout_seed", u64), ("tile_slot", ptr), ("tile_rank", ptr),
-                ("trace", ptr), ("trace_cap", i32)]
+                ("trace", ptr), ("trace_cap", i32), ("inflight", i32)]
 
 
 class BiLstmBf16Params(C.Structure):

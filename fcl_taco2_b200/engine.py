@@ -75,15 +75,22 @@ class Engine:
                 self.blstm_whh_bf16 = _pack.pack_bilstm_whh_bf16(packed).to(self.device)
             self.n_slots = _lib.load().fcl_sm_count()
             priv_b, shared_b, c_f = _lib.decoder_bf16_workspace(hp.prenet_units, hp.dunits)
-            self.dec_act_priv = torch.empty((self.n_slots * priv_b,), dtype=torch.uint8, device=self.device)
+            # two blocks per CTA: the pair kernel keeps two super-tiles in flight (x1|x2 images and cell state per slot)
+            self.dec_act_priv = torch.empty((2 * self.n_slots * priv_b,), dtype=torch.uint8, device=self.device)
             self.dec_act_shared = torch.empty((self.n_slots * shared_b,), dtype=torch.uint8, device=self.device)
-            self.dec_c_ws = torch.empty((self.n_slots * c_f,), dtype=torch.float32, device=self.device)
+            self.dec_c_ws = torch.empty((2 * self.n_slots * c_f,), dtype=torch.float32, device=self.device)
             self.dec_group_sync = torch.zeros((2 * self.n_slots,), dtype=torch.int32, device=self.device)
         self.head_b = {s: float(packed[f"{s}_head_b"][0]) for s in ("dur", "pitch", "energy")}
         self.launches = 0
         self._arena, self._arena_views, self._arena_seq, self._in_pass = [], [], 0, False
         self._stream_handle = None
         self.force_group = 0             # decoder group size override (tests); 0 = choose from the tile count
+        self.max_pairs = None            # tests: fewer CTA pairs than SMs / 2, so that every pair walks many super-tiles
+        # super-tiles a CTA pair of the cta_group::2 decoder keeps in flight. 2 is implemented and bit-identical
+        # (tests/test_gpu_scale.py) but measured SLOWER (S batch 1024: 1.73 -> 1.98 ms): the operand stream, not the phase
+        # boundaries, bounds the kernel (all 148 SMs pull 32 KB per K stage through L2: ~6.4 KB/clk chip-wide, the L2 ->
+        # SM ceiling), and a second tile in flight doubles the scratch working set (profiles/r02_decoder_inflight.md)
+        self.pair_inflight = 1
         self.use_pair = None             # cta_group::2 decoder (CTA pairs): None = when every SM has a tile anyway; True / False force it
         self.skip_zero_durations = False # extension: phonemes with d = 0 produce no frames (the reference's inference asserts)
         self.use_img_convs = bool(getattr(self, "wi", None))   # padded-row-space image convolutions for encoder + predictors
@@ -373,7 +380,7 @@ class Engine:
         if use_pair and group == 1 and n_tiles >= 2:
             # cta_group::2: pairs of CTAs walk super-tiles of 256 rows
             n_super = (n_tiles + 1) // 2
-            n_pairs = min(self.n_slots // 2, n_super)
+            n_pairs = min(self.max_pairs or self.n_slots // 2, self.n_slots // 2, n_super)
             sched = self._buf((2, n_super), torch.int32)
             self._call("fcl_decoder_schedule", _lib.DecoderScheduleParams(n_rows=P, n_tiles=n_super, n_slots=n_pairs,
                                                                           unit_rows=256, order=dptr(order), dur=dptr(dur),
@@ -412,7 +419,8 @@ class Engine:
                                    zoneout=zoneout,
                                    dropout_p=dropout_p, dropout_seed=dropout_seed, tile_slot=dptr(sched[0]),
                                    tile_rank=dptr(sched[1]), trace=dptr(trace),
-                                   trace_cap=(trace.numel() - 2) // 2 if trace is not None else 0)
+                                   trace_cap=(trace.numel() - 2) // 2 if trace is not None else 0,
+                                   inflight=self.pair_inflight)
         with self.stage("decoder_loop"):
             self._call("fcl_decoder_bf16_pair" if group < 0 else "fcl_decoder_bf16", p)
         return before

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 18
+#define FCL_ABI_VERSION 19
 
 enum {
   FCL_OK = 0,
@@ -410,6 +410,8 @@ typedef struct {
   const int32_t* tile_rank;  /* (n_tiles) position of the tile in its slot's list                             */
   int64_t* trace;            /* optional debug timeline of CTA 0: [0] = count (zero it), then (id, clock) pairs */
   int32_t trace_cap;         /* capacity in records                                         */
+  int32_t inflight;          /* fcl_decoder_bf16_pair: super-tiles a CTA pair keeps in flight (1 or 2; 0 = 1). With 2,
+                                act_priv and c_ws hold TWO blocks per CTA (2 * priv_bytes_per_cta, 2 * c_floats_per_cta). */
 } FclDecoderBf16Params;
 /* Longest-processing-time assignment of the duration-sorted tiles to the persistent CTAs (tile cost = its
  * step count + 1): every CTA ends at about the same time. One warp, ~20 us. */
@@ -430,6 +432,7 @@ int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream);
  * `group` is ignored, tile_slot/tile_rank are indexed by super-tile (fcl_decoder_schedule with unit_rows = 256,
  * n_slots = number of pairs), act_shared holds n_slots * shared_bytes_per_group, and w_stream uses the pair packing
  * (pack.py: pack_decoder_stream(pair=True): each stage block = [half 0][half 1], feat_out columns padded to 128). */
+/* act_priv / c_ws are indexed with TWO blocks per CTA in this kernel whatever `inflight` is. */
 int fcl_decoder_bf16_pair(const FclDecoderBf16Params* p, void* stream);
 
 /* ---------------------------------------------------------------- multi-GPU: peer-memory gather plumbing

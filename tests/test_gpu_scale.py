@@ -113,6 +113,37 @@ def test_decoder_kernel_multi_tile_routes(kind, n_rows):
     assert worst[0] < DEC_MAX_ABS and worst[1] < DEC_MEAN_L1, worst
 
 
+@pytest.mark.parametrize("kind,max_pairs,n_rows", [("S", 3, 40 * 128 + 50), ("S", 1, 9 * 128), ("S", 5, 23 * 128 + 1), ("T", 2, 13 * 128)])
+def test_decoder_two_super_tiles_in_flight(kind, max_pairs, n_rows):
+    """A few CTA pairs walking MANY super-tiles with two of them in flight: slots refill at different steps (ragged step
+    counts), the list ends with a single active slot, odd tile counts leave the last peer a dummy tile. inflight = 2 must
+    equal inflight = 1 and the single-CTA kernel bit for bit."""
+    from fcl_taco2_b200.engine import Engine
+    hp = hparams.preset(kind)
+    sd = weights(kind, 0)
+    eng = Engine(hp, pack.pack_fp32(sd, hp), "cuda:0", "bf16")
+    rs = np.random.RandomState(n_rows)
+    lens = []
+    while sum(lens) < n_rows:
+        lens.append(int(min(rs.randint(5, 150), n_rows - sum(lens))))
+    xs = [synth.phoneme_ids(n, 76, rs) for n in lens]
+    ds = [np.clip(rs.geometric(0.25, size=n), 1, 30 if kind == "S" else 9).astype(np.int64) for n in lens]   # skewed: few long rows
+    pl = planmod.make_plan(xs, ds)
+    d, _ = eng.upload(pl)
+    hn = torch.randn(pl.n_rows, hp.eunits, generator=torch.Generator().manual_seed(5)).cuda()
+    frame_off, ufo, order, totals = eng.len_reg_scan(d["dur"], d["utt_off"], pl.n_utts)
+    F_ = int(pl.dur.sum())
+    outs = {}
+    for name, pair, infl, mp in (("single", False, 1, None), ("pair1", True, 1, max_pairs), ("pair2", True, 2, max_pairs)):
+        eng.use_pair, eng.force_group, eng.pair_inflight, eng.max_pairs = pair, 1, infl, mp
+        outs[name] = eng.decoder(hn, d["dur"], frame_off, order, d["row_utt"], d["row_phone"], F_, 0.1, 0.5, 31).clone()
+    eng.use_pair, eng.force_group, eng.pair_inflight, eng.max_pairs = None, 0, 1, None
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs["pair2"]).all()
+    assert torch.equal(outs["pair1"], outs["single"])
+    assert torch.equal(outs["pair2"], outs["single"]), float((outs["pair2"] - outs["single"]).abs().max())
+
+
 def test_t_batch32_group_mode_vs_oracle():
     """BASELINE config 2: FCL-taco2-T, batch 32 (20 tiles: the engine picks group mode, g = 7) vs the oracle."""
     m = _model("T", 0, 7)
