@@ -393,6 +393,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip latency, secondary configs and the strong-scaling arm")
     ap.add_argument("--pair", type=int, default=-1, help="cta_group::2 decoder: 1 on, 0 off, -1 engine default")
+    ap.add_argument("--pair-kernel", default="", choices=["", "v1", "v2"], help="cta_group::2 decoder variant (default: engine's)")
+    ap.add_argument("--inflight", type=int, default=0, help="super-tiles in flight per CTA pair (v2 kernel; 0 = engine default)")
     ap.add_argument("--e2e-planner", type=int, default=0, help="inference_stream: plan batches in a helper thread (1) or inline (0)")
     ap.add_argument("--dropout", type=float, default=0.5, help="prenet dropout rate (reference default 0.5)")
     ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "peer"], help="N > 1: transport of the final mel gather")
@@ -422,6 +424,10 @@ def main():
     eng = m.engine()
     if args.pair >= 0:
         eng.use_pair = bool(args.pair)
+    if args.pair_kernel:
+        eng.pair_kernel = args.pair_kernel
+    if args.inflight:
+        eng.pair_inflight = args.inflight
     xs, ds = workload(args, rank)
     arm = Arm(m, xs, ds)
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)

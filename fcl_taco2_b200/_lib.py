@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -109,14 +109,16 @@ class PadRowsParams(C.Structure):
 
 
 class RowsToImageParams(C.Structure):
-    _fields_ = [("n_tiles", i32), ("chans", i32), ("src", ptr), ("ld", i32), ("gather", ptr), ("prow_src", ptr), ("img", ptr)]
+    _fields_ = [("n_tiles", i32), ("chans", i32), ("src", ptr), ("ld", i32), ("gather", ptr), ("prow_src", ptr), ("img", ptr),
+                ("src_chans", i32)]
 
 
 class ConvImgParams(C.Structure):
     _fields_ = [("n_tiles", i32), ("cin", i32), ("cout", i32), ("taps", i32), ("nb", i32), ("act", i32), ("epi", i32),
                 ("in_img", ptr), ("w_packed", ptr), ("bias", ptr), ("prow_src", ptr), ("out_img", ptr), ("out_blk", ptr),
                 ("gamma", ptr), ("beta", ptr), ("head_w", ptr), ("head_b", f32), ("head_out", ptr), ("dur_out", ptr),
-                ("n_pairs", i32), ("trace", ptr), ("trace_cap", i32)]
+                ("n_pairs", i32), ("trace", ptr), ("trace_cap", i32), ("out_rows", ptr), ("ldo", i32), ("out_chans", i32),
+                ("residual", ptr), ("ldr", i32)]
 
 
 class DecoderScheduleParams(C.Structure):
@@ -147,6 +149,7 @@ ENTRY_POINTS = {
     "fcl_conv_tiles": ConvTilesParams,
     "fcl_decoder_schedule": DecoderScheduleParams,
     "fcl_decoder_bf16_pair": DecoderBf16Params,
+    "fcl_decoder_bf16_pair_v1": DecoderBf16Params,
     "fcl_conv_stack_tiles": ConvStackTilesParams,
     "fcl_conv_stack_bf16": ConvStackParams,
     "fcl_pad_rows": PadRowsParams,
@@ -158,7 +161,7 @@ PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_last_error", "fcl_sm_count", "fcl_struc
                  "fcl_ipc_close", "fcl_copy_async", "fcl_wait_flags", "fcl_write_flags"]
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
-EPI_IMAGE, EPI_LN_IMAGE, EPI_LN_HEAD, EPI_BLOCKED_F32, EPI_BLOCKED_F16 = 0, 1, 2, 3, 4
+EPI_IMAGE, EPI_LN_IMAGE, EPI_LN_HEAD, EPI_BLOCKED_F32, EPI_BLOCKED_F16, EPI_ROWS_F32 = 0, 1, 2, 3, 4, 5
 PAD_GAP = 2            # zero rows between utterances in the padded row space (halo of the k <= 5 convolutions)
 MAX_DURATION = 1023
 

@@ -275,7 +275,7 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
       long zrow = -1;
       if (tile == 0 && r < kRowOff) zrow = r;
       else if (tile == p.n_tiles - 1 && r >= 128 - kRowOff) zrow = (long)p.n_tiles * 128 + kRowOff + (r - (128 - kRowOff));
-      if constexpr (EPI == FCL_EPI_IMAGE || EPI == FCL_EPI_BLOCKED_F32 || EPI == FCL_EPI_BLOCKED_F16) {
+      if constexpr (EPI == FCL_EPI_IMAGE || EPI == FCL_EPI_BLOCKED_F32 || EPI == FCL_EPI_BLOCKED_F16 || EPI == FCL_EPI_ROWS_F32) {
         const int n_acc = whole_row ? 1 : nblk;
         for (int a = 0; a < n_acc; ++a) {
           const uint32_t buf = acc_ctr % (uint32_t)n_bufs, use = acc_ctr / (uint32_t)n_bufs;
@@ -303,6 +303,19 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                 uint8_t* o = orow + (size_t)(c0 >> 3) * slab_stride;
                 *reinterpret_cast<uint4*>(o) = w0;
                 *reinterpret_cast<uint4*>(o + slab_stride) = w1;
+              }
+            } else if constexpr (EPI == FCL_EPI_ROWS_F32) {
+              if (live && c0 < p.out_chans) {
+                float4* o = reinterpret_cast<float4*>(p.out_rows + (size_t)src * p.ldo + c0);
+                const float4* res = p.residual ? reinterpret_cast<const float4*>(p.residual + (size_t)src * p.ldr + c0) : nullptr;
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                  if (c0 + 4 * qd < p.out_chans) {
+                    float4 x = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+                    if (res) { const float4 rr = __ldg(res + qd); x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w; }
+                    o[qd] = x;
+                  }
+                }
               }
             } else if constexpr (EPI == FCL_EPI_BLOCKED_F32) {
               if (live) {
@@ -465,6 +478,7 @@ __global__ void __launch_bounds__(256)
 rows_to_image_kernel(FclRowsToImageParams p) {
   const long rows_alloc = (long)p.n_tiles * 128 + 8;
   const int slabs = p.chans >> 3;
+  const int src_chans = p.src_chans > 0 ? p.src_chans : p.chans;
   const long total = rows_alloc * slabs;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int slab = (int)(i / rows_alloc);
@@ -473,7 +487,7 @@ rows_to_image_kernel(FclRowsToImageParams p) {
     int src = -1;
     if (prow >= 0 && prow < (long)p.n_tiles * 128) src = __ldg(p.prow_src + prow);
     uint4 w = make_uint4(0u, 0u, 0u, 0u);
-    if (src >= 0) {
+    if (src >= 0 && slab * 8 < src_chans) {
       const size_t row = p.gather ? (size_t)__ldg(p.gather + src) : (size_t)src;
       const float4* s = reinterpret_cast<const float4*>(p.src + row * p.ld + (size_t)slab * 8);
       const float4 a = __ldg(s), b = __ldg(s + 1);
@@ -516,6 +530,7 @@ extern "C" int fcl_rows_to_image(const FclRowsToImageParams* p, void* stream) {
   using namespace fcl;
   FCL_REQUIRE(p && p->src && p->prow_src && p->img, "null pointer");
   FCL_REQUIRE(p->n_tiles > 0 && p->chans > 0 && p->chans % 8 == 0 && p->ld % 4 == 0, "bad sizes");
+  FCL_REQUIRE(p->src_chans >= 0 && p->src_chans <= p->chans && p->src_chans % 8 == 0, "src_chans must be a multiple of 8, <= chans");
   const long total = ((long)p->n_tiles * 128 + 8) * (p->chans / 8);
   int sms = fcl_sm_count();
   if (sms < 0) return sms;
@@ -533,7 +548,10 @@ extern "C" int fcl_conv_img_bf16(const FclConvImgParams* p, void* stream) {
   FCL_REQUIRE(p->nb >= 64 && p->nb <= 256 && p->nb % 64 == 0 && p->cout % p->nb == 0, "nb must be a multiple of 64 (<= 256) dividing cout");
   FCL_REQUIRE(p->cout <= 2048, "cout must be <= 2048");
   const bool ln = p->epi == FCL_EPI_LN_IMAGE || p->epi == FCL_EPI_LN_HEAD;
-  FCL_REQUIRE(p->epi >= FCL_EPI_IMAGE && p->epi <= FCL_EPI_BLOCKED_F16, "unknown epilogue");
+  FCL_REQUIRE(p->epi >= FCL_EPI_IMAGE && p->epi <= FCL_EPI_ROWS_F32, "unknown epilogue");
+  FCL_REQUIRE(p->epi != FCL_EPI_ROWS_F32 || (p->out_rows && p->out_chans > 0 && p->out_chans <= p->cout && p->out_chans % 4 == 0 &&
+                                              p->ldo % 4 == 0 && (!p->residual || p->ldr % 4 == 0)),
+              "row epilogue needs out_rows, out_chans (multiple of 4, <= cout) and leading dimensions that are multiples of 4");
   FCL_REQUIRE(!ln || (p->cout <= 512 && p->gamma && p->beta), "LayerNorm epilogues need gamma/beta and cout <= 512");
   FCL_REQUIRE(!ln || p->cout <= 256 || p->cout == 2 * p->nb, "LayerNorm rows wider than 256 columns must be exactly two N blocks");
   FCL_REQUIRE(p->epi != FCL_EPI_LN_HEAD || (p->head_w && (p->head_out || p->dur_out)), "head epilogue needs head_w and an output");
@@ -582,8 +600,9 @@ extern "C" int fcl_conv_img_bf16(const FclConvImgParams* p, void* stream) {
   else if (p->epi == FCL_EPI_LN_IMAGE) kern = act == FCL_ACT_RELU ? conv_img_kernel<FCL_EPI_LN_IMAGE, FCL_ACT_RELU> : conv_img_kernel<FCL_EPI_LN_IMAGE, FCL_ACT_NONE>;
   else if (p->epi == FCL_EPI_LN_HEAD) kern = act == FCL_ACT_RELU ? conv_img_kernel<FCL_EPI_LN_HEAD, FCL_ACT_RELU> : conv_img_kernel<FCL_EPI_LN_HEAD, FCL_ACT_NONE>;
   else if (p->epi == FCL_EPI_BLOCKED_F32) kern = act == FCL_ACT_RELU ? conv_img_kernel<FCL_EPI_BLOCKED_F32, FCL_ACT_RELU> : conv_img_kernel<FCL_EPI_BLOCKED_F32, FCL_ACT_NONE>;
+  else if (p->epi == FCL_EPI_ROWS_F32) kern = act == FCL_ACT_RELU ? conv_img_kernel<FCL_EPI_ROWS_F32, FCL_ACT_RELU> : act == FCL_ACT_TANH ? conv_img_kernel<FCL_EPI_ROWS_F32, FCL_ACT_TANH> : conv_img_kernel<FCL_EPI_ROWS_F32, FCL_ACT_NONE>;
   else kern = act == FCL_ACT_RELU ? conv_img_kernel<FCL_EPI_BLOCKED_F16, FCL_ACT_RELU> : conv_img_kernel<FCL_EPI_BLOCKED_F16, FCL_ACT_NONE>;
-  FCL_REQUIRE(act == FCL_ACT_NONE || act == FCL_ACT_RELU || (act == FCL_ACT_TANH && p->epi == FCL_EPI_IMAGE), "unsupported activation for this epilogue");
+  FCL_REQUIRE(act == FCL_ACT_NONE || act == FCL_ACT_RELU || (act == FCL_ACT_TANH && (p->epi == FCL_EPI_IMAGE || p->epi == FCL_EPI_ROWS_F32)), "unsupported activation for this epilogue");
   if (int rc = ensure_dyn_smem_fn(reinterpret_cast<const void*>(kern), smem, "fcl_conv_img_bf16")) return rc;
   int sms = fcl_sm_count();
   if (sms < 0) return sms;

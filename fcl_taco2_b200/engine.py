@@ -68,6 +68,9 @@ class Engine:
             self.bf16_decoder = bf16_decoder
             # front end as image-to-image convolutions (csrc/conv_img_bf16.cu) when every GEMM runs in bf16
             self.wi = {k: (t.to(self.device), nb) for k, (t, nb) in _pack.pack_img(packed).items()} if bf16_gemms is None else {}
+            # postnet layers for the same kernel (channels zero-padded to multiples of 64): (weights, nb, cin, cout, bias)
+            self.wpost = {k: (t.to(self.device), nb, ci, co, b.to(self.device))
+                          for k, (t, nb, ci, co, b) in _pack.pack_img_postnet(packed).items()} if bf16_gemms is None else {}
             self.dec_stream = _pack.pack_decoder_stream(packed, hp).to(self.device)
             self.dec_stream_pair = _pack.pack_decoder_stream(packed, hp, pair=True).to(self.device)
             self.blstm_whh_bf16 = None
@@ -85,15 +88,16 @@ class Engine:
         self._arena, self._arena_views, self._arena_seq, self._in_pass = [], [], 0, False
         self._stream_handle = None
         self.force_group = 0             # decoder group size override (tests); 0 = choose from the tile count
+        # cta_group::2 decoder variant: "v1" = one super-tile per CTA pair at a time (per-role tile loops); "v2" = slot
+        # scheduler with `pair_inflight` super-tiles in flight. Both are bit-identical and tested; v1 is the faster one
+        # (S batch 1024: v1 1.78 ms, v2 2.01 / 1.99 ms with 1 / 2 in flight -- profiles/r02_decoder_inflight.md)
+        self.pair_kernel = "v1"
         self.max_pairs = None            # tests: fewer CTA pairs than SMs / 2, so that every pair walks many super-tiles
-        # super-tiles a CTA pair of the cta_group::2 decoder keeps in flight. 2 is implemented and bit-identical
-        # (tests/test_gpu_scale.py) but measured SLOWER (S batch 1024: 1.73 -> 1.98 ms): the operand stream, not the phase
-        # boundaries, bounds the kernel (all 148 SMs pull 32 KB per K stage through L2: ~6.4 KB/clk chip-wide, the L2 ->
-        # SM ceiling), and a second tile in flight doubles the scratch working set (profiles/r02_decoder_inflight.md)
-        self.pair_inflight = 1
+        self.pair_inflight = 2           # v2 only
         self.use_pair = None             # cta_group::2 decoder (CTA pairs): None = when every SM has a tile anyway; True / False force it
         self.skip_zero_durations = False # extension: phonemes with d = 0 produce no frames (the reference's inference asserts)
         self.use_img_convs = bool(getattr(self, "wi", None))   # padded-row-space image convolutions for encoder + predictors
+        self.use_img_postnet = bool(getattr(self, "wpost", None))   # ... and for the postnet (five launches, any channel width)
         self.use_encoder_stack = False   # measured: with 256 channels only a 2-stage weight ring fits beside the images
         self.stage_events = None      # when a list: (stage, start_event, stop_event) appended per stage (bench.py)
 
@@ -190,18 +194,18 @@ class Engine:
                                                       n_tiles=n_tiles, prow_src=dptr(prow_src), prow_off=dptr(prow_off)))
         return {"n_tiles": n_tiles, "rows_alloc": n_tiles * 128 + 8, "prow_src": prow_src, "prow_off": prow_off}
 
-    def rows_to_image(self, src, ld, chans, pad, gather=None):
+    def rows_to_image(self, src, ld, chans, pad, gather=None, src_chans=0):
         img = self._buf((chans // 8 * pad["rows_alloc"] * 8,), torch.bfloat16)
         self._call("fcl_rows_to_image", _lib.RowsToImageParams(n_tiles=pad["n_tiles"], chans=chans, src=dptr(src), ld=ld,
                                                                gather=dptr(gather), prow_src=dptr(pad["prow_src"]),
-                                                               img=dptr(img)))
+                                                               img=dptr(img), src_chans=src_chans))
         return img
 
     def conv_img(self, key, in_img, pad, cin, cout, taps, act, epi, bias=None, gamma=None, beta=None, head_w=None,
-                 head_b=0.0, head_out=None, dur_out=None):
-        """One image-to-image conv launch. -> the output image (EPI_IMAGE / EPI_LN_IMAGE), the blocked fp32 buffer
-        (EPI_BLOCKED_F32) or None (EPI_LN_HEAD: results are in head_out / dur_out)."""
-        wp, nb = self.wi[key]
+                 head_b=0.0, head_out=None, dur_out=None, weights=None, out_rows=None, out_chans=0, residual=None):
+        """One image-to-image conv launch. -> the output image (EPI_IMAGE / EPI_LN_IMAGE), the blocked buffer
+        (EPI_BLOCKED_*) or None (EPI_LN_HEAD: results are in head_out / dur_out; EPI_ROWS_F32: in out_rows)."""
+        wp, nb = weights if weights is not None else self.wi[key]
         out_img = out_blk = None
         if epi in (_lib.EPI_IMAGE, _lib.EPI_LN_IMAGE):
             out_img = self._buf((cout // 8 * pad["rows_alloc"] * 8,), torch.bfloat16)
@@ -213,7 +217,8 @@ class Engine:
             n_tiles=pad["n_tiles"], cin=cin, cout=cout, taps=taps, nb=nb, act=act, epi=epi, in_img=dptr(in_img),
             w_packed=dptr(wp), bias=dptr(bias), prow_src=dptr(pad["prow_src"]), out_img=dptr(out_img), out_blk=dptr(out_blk),
             gamma=dptr(gamma), beta=dptr(beta), head_w=dptr(head_w), head_b=head_b, head_out=dptr(head_out),
-            dur_out=dptr(dur_out), n_pairs=0))
+            dur_out=dptr(dur_out), n_pairs=0, out_rows=dptr(out_rows), ldo=out_rows.shape[1] if out_rows is not None else 0,
+            out_chans=out_chans, residual=dptr(residual), ldr=residual.shape[1] if residual is not None else 0))
         return out_img if out_img is not None else out_blk
 
     # ------------------------------------------------------------------ stages
@@ -422,7 +427,8 @@ class Engine:
                                    trace_cap=(trace.numel() - 2) // 2 if trace is not None else 0,
                                    inflight=self.pair_inflight)
         with self.stage("decoder_loop"):
-            self._call("fcl_decoder_bf16_pair" if group < 0 else "fcl_decoder_bf16", p)
+            self._call(("fcl_decoder_bf16_pair_v1" if self.pair_kernel == "v1" else "fcl_decoder_bf16_pair") if group < 0
+                       else "fcl_decoder_bf16", p)
         return before
 
     def conv_stack(self, keys, acts, x, ld_in, rows, seg_off, n_segs, max_len_sum_tiles, taps=5, gather=None,
@@ -469,6 +475,24 @@ class Engine:
         consumer (the multi-GPU gather, a D2H copy) can start on finished frames while later chunks still compute."""
         hp, w = self.hp, self.w
         O, C = hp.odim, hp.postnet_chans
+        if self.precision == "bf16" and self.use_img_postnet and len(fseg) > 3 and n_frames > 0:
+            # five image-to-image launches in the padded FRAME space (decoder_sa.py:274-286): the mel input is converted
+            # once (80 -> 128 zero-padded channels), activations stay bf16 images, the last layer writes fp32 rows and
+            # adds the residual (decoder_sa.py:632)
+            utt_frame_off, n_utts = fseg[3]
+            pad = self.pad_rows(utt_frame_off, n_utts, n_frames)
+            x = self.rows_to_image(before, O, self.wpost["post_conv0"][2], pad, src_chans=O)
+            for l in range(4):
+                wp, nb, ci, co, b = self.wpost[f"post_conv{l}"]
+                x = self.conv_img(None, x, pad, ci, co, 5, ACT_TANH, _lib.EPI_IMAGE, bias=b, weights=(wp, nb))
+            wp, nb, ci, co, b = self.wpost["post_conv4"]
+            final = torch.empty((n_frames, O), dtype=torch.float32, device=self.device)     # returned to the caller
+            self.conv_img(None, x, pad, ci, co, 5, ACT_NONE, _lib.EPI_ROWS_F32, bias=b, weights=(wp, nb), out_rows=final,
+                          out_chans=O, residual=before)
+            if chunks and chunk_cb is not None:
+                for k, (u0, u1, f0, f1) in enumerate(chunks):          # one launch sequence: hand everything over at the end
+                    chunk_cb(k, final, f0, f1)
+            return final
         stack_ok = self.precision == "bf16" and len(fseg) > 3 and all(f"post_conv{l}" in self.wb for l in range(5))
         if stack_ok and chunks and chunk_cb is not None:
             utt_frame_off, n_utts = fseg[3]
@@ -604,12 +628,15 @@ class Engine:
                 frame_off, utt_frame_off, order, totals = self.len_reg_scan(dur, d["utt_off"], B)
             sched = self.decoder_schedule(order, dur, P) if self.precision == "bf16" and self.bf16_decoder else None
             fmap = pos = ftiles = None
-            if F is not None:
+            if F is not None and need_fmap:
                 with self.stage("frame_map"):
                     fmap, pos = self.frame_map(frame_off, utt_frame_off, P, B, F, want_position=extras)
                     ftiles = self.conv_tiles(utt_frame_off, B, (F + 127) // 128 + B)
             return frame_off, utt_frame_off, order, totals, sched, fmap, pos, ftiles
 
+        # the frame -> (row, step) map and the per-utterance frame tiles only serve the layer-by-layer / fused-stack postnet
+        # (and the diagnostics of `extras`); the image postnet works from the frame offsets alone
+        need_fmap = extras or not (self.precision == "bf16" and self.use_img_postnet)
         lr = None
         if not need_pred_dur:
             if not self.skip_zero_durations and (plan.dur == 0).any():
@@ -657,9 +684,11 @@ class Engine:
                                  "(nets/modules/decoder_sa.py:575); pass dur= or skip_zero_durations=True")
             if F == 0:
                 raise ValueError("every predicted duration is zero: no frames to decode")
-            with self.stage("frame_map"):
-                fmap, pos = self.frame_map(frame_off, utt_frame_off, P, B, F, want_position=extras)
-                ftiles = self.conv_tiles(utt_frame_off, B, (F + 127) // 128 + B)
+            fmap = pos = ftiles = None
+            if need_fmap:
+                with self.stage("frame_map"):
+                    fmap, pos = self.frame_map(frame_off, utt_frame_off, P, B, F, want_position=extras)
+                    ftiles = self.conv_tiles(utt_frame_off, B, (F + 127) // 128 + B)
         else:
             frame_off, utt_frame_off, order, totals, sched, fmap, pos, ftiles = lr
             if use_side:
@@ -668,7 +697,8 @@ class Engine:
                               dropout_seed, tile_rows, schedule=sched)
         with self.stage("postnet"):
             chunks = output_chunks(ufo, out_chunks) if (out_chunks and chunk_cb is not None) else None
-            out = self.postnet(before, (fmap[2], fmap[3], ftiles, (utt_frame_off, B)), F, chunks, chunk_cb)
+            out = self.postnet(before, (fmap[2] if fmap is not None else None, fmap[3] if fmap is not None else None, ftiles,
+                                        (utt_frame_off, B)), F, chunks, chunk_cb)
         if extras:
             ex.update(h=h, dlog=dlog, dur_pred=dur_pred, pitch=pitch, energy=energy, hn=hn, before=before,
                       frame_off=frame_off, order=order, frame_row=fmap[0], frame_step=fmap[1], position=pos,

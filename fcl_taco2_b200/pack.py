@@ -152,6 +152,35 @@ def pack_img(packed_fp32: dict) -> dict:
     return out
 
 
+def _pad_to(x: torch.Tensor, dim: int, mult: int) -> torch.Tensor:
+    n = x.shape[dim]
+    m = (n + mult - 1) // mult * mult
+    if m == n:
+        return x
+    shape = list(x.shape)
+    shape[dim] = m
+    out = torch.zeros(shape, dtype=x.dtype)
+    out.narrow(dim, 0, n).copy_(x)
+    return out
+
+
+def pack_img_postnet(packed_fp32: dict) -> dict:
+    """Postnet layers (decoder_sa.py:176-263: Conv1d k5 no bias + BatchNorm eval, folded) for the image convolutions:
+    input / output channels zero-padded to multiples of 64 (80 -> 128 mel channels). -> {key: (weights, nb, cin, cout, bias)}
+    or {} when a layer does not fit the kernel."""
+    out = {}
+    try:
+        for l in range(5):
+            w = _pad_to(_pad_to(packed_fp32[f"post_conv{l}_w"], 1, 64), 2, 64)
+            if w.shape[1] > 512 or w.shape[2] > 2048 or w.shape[0] != 5:
+                return {}
+            wp, nb = pack_conv_pair(w)
+            out[f"post_conv{l}"] = (wp, nb, w.shape[1], w.shape[2], _pad_to(packed_fp32[f"post_conv{l}_b"], 0, 64).contiguous())
+    except (ValueError, AssertionError):
+        return {}
+    return out
+
+
 STACK_KSTAGE = 32
 
 GEMM_KEYS = ["enc_conv0", "enc_conv1", "enc_conv2", "blstm_wih", "dur_conv0", "dur_conv1", "pitch_conv0", "pitch_conv1",

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 19
+#define FCL_ABI_VERSION 20
 
 enum {
   FCL_OK = 0,
@@ -212,6 +212,7 @@ typedef struct {
   const int64_t* gather;         /* optional: source row = gather[original row] (torch.nn.Embedding ids)          */
   const int32_t* prow_src;       /* (n_tiles*128) from fcl_pad_rows                                               */
   void* img;                     /* out bf16 [chans/8][n_tiles*128 + 8][8]                                        */
+  int32_t src_chans;             /* channels present in `src` (multiple of 8); image channels beyond are zero. 0 = chans */
 } FclRowsToImageParams;
 int fcl_rows_to_image(const FclRowsToImageParams* p, void* stream);
 
@@ -220,7 +221,9 @@ enum {
   FCL_EPI_LN_IMAGE = 1,     /* LayerNorm_C(act(conv + bias)) * gamma + beta -> bf16 image (variance_predictor.py:52-64) */
   FCL_EPI_LN_HEAD = 2,      /* ... -> dot(., head_w) + head_b -> head_out[original row] (+ duration rounding)      */
   FCL_EPI_BLOCKED_F32 = 3,  /* conv + bias -> fp32, column-blocked by PADDED row: out[c/16][n_tiles*128][c%16]     */
-  FCL_EPI_BLOCKED_F16 = 4   /* same layout in fp16 (saturating): half the HBM bytes, 11-bit significand            */
+  FCL_EPI_BLOCKED_F16 = 4,  /* same layout in fp16 (saturating): half the HBM bytes, 11-bit significand            */
+  FCL_EPI_ROWS_F32 = 5      /* act(conv + bias) (+ residual) -> fp32 rows by ORIGINAL row: out_rows[row][c], c < out_chans
+                               (last postnet layer + `before` residual: decoder_sa.py:285,632)                      */
 };
 typedef struct {
   int32_t n_tiles, cin, cout, taps;   /* cin % 64 == 0; taps in {1,3,5}                                           */
@@ -241,6 +244,10 @@ typedef struct {
   int32_t n_pairs;                    /* CTA pairs to launch; 0 = min(SMs / 2, ceil(n_tiles / 2))                  */
   int64_t* trace;                     /* optional debug timeline of CTA 0: [0] = count (zero it), then (id, clock) pairs */
   int32_t trace_cap;                  /* capacity in records                                                        */
+  float* out_rows;                    /* FCL_EPI_ROWS_F32: (n_rows, ldo) fp32                                       */
+  int32_t ldo, out_chans;             /* out_chans <= cout, multiple of 4 (cout may be zero-padded to a multiple of 64) */
+  const float* residual;              /* optional (n_rows, ldr), added after the activation                         */
+  int32_t ldr;
 } FclConvImgParams;
 int fcl_conv_img_bf16(const FclConvImgParams* p, void* stream);
 
@@ -434,6 +441,9 @@ int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream);
  * (pack.py: pack_decoder_stream(pair=True): each stage block = [half 0][half 1], feat_out columns padded to 128). */
 /* act_priv / c_ws are indexed with TWO blocks per CTA in this kernel whatever `inflight` is. */
 int fcl_decoder_bf16_pair(const FclDecoderBf16Params* p, void* stream);
+/* Round-1 form of the same kernel (one super-tile per pair at a time, per-role tile loops instead of the slot scheduler):
+ * same parameters and results; `inflight` is ignored and act_priv / c_ws are indexed with ONE block per CTA. */
+int fcl_decoder_bf16_pair_v1(const FclDecoderBf16Params* p, void* stream);
 
 /* ---------------------------------------------------------------- multi-GPU: peer-memory gather plumbing
  * The path shards by utterance with no collective on the hot path; the one exchange is the final

@@ -182,8 +182,17 @@ def test_fused_postnet_stack_matches_layer_by_layer(bf16_engines):
     ufo = torch.from_numpy(off).cuda()
     tiles = eng.conv_tiles(ufo, len(lens), sum((n + 127) // 128 for n in lens))
     ref = eng.postnet(before, (lo, hi, tiles), F_)                          # layer by layer
+    eng.use_img_postnet = False
     fused = eng.postnet(before, (lo, hi, tiles, (ufo, len(lens))), F_)      # fused stack
+    eng.use_img_postnet = True
+    img = eng.postnet(before, (lo, hi, tiles, (ufo, len(lens))), F_)        # five image-to-image launches (engine default)
     torch.cuda.synchronize()
+    assert torch.isfinite(img).all()
+    mx_i, mean_i = err(img.cpu(), ref.cpu())
+    assert mx_i < 3e-2 and mean_i < 2e-3, (mx_i, mean_i)                    # same bf16 roundings, different summation order
+    for k in range(len(lens)):
+        o = restate.postnet(sd, before[off[k]:off[k + 1]].cpu())
+        assert err(img[off[k]:off[k + 1]].cpu(), o)[0] < 8e-2
     assert torch.isfinite(fused).all()
     # The fused stack pads the first layer's K to 128 (different fp32 summation order): a handful of layer-0 outputs
     # round to the neighbouring bf16 value and each flip fans out over +-8 rows by the last layer (tools/dbg_stack.py:
@@ -208,11 +217,13 @@ def test_chunked_postnet_bit_identical(bf16_engines):
     ufo = torch.from_numpy(off).cuda()
     tiles = eng.conv_tiles(ufo, len(lens), sum((n + 127) // 128 for n in lens))
     fseg = (lo, hi, tiles, (ufo, len(lens)))
+    eng.use_img_postnet = False                                             # the fused stack is the chunkable variant
     whole = eng.postnet(before, fseg, F_)
     seen = []
     chunks = planmod.output_chunks(off, 4)
     assert len(chunks) >= 3
     chunked = eng.postnet(before, fseg, F_, chunks, lambda k, out, f0, f1: seen.append((k, f0, f1)))
+    eng.use_img_postnet = True
     torch.cuda.synchronize()
     assert seen == [(k, c[2], c[3]) for k, c in enumerate(chunks)]
     assert torch.equal(whole, chunked)

@@ -117,7 +117,7 @@ def test_decoder_kernel_multi_tile_routes(kind, n_rows):
 def test_decoder_two_super_tiles_in_flight(kind, max_pairs, n_rows):
     """A few CTA pairs walking MANY super-tiles with two of them in flight: slots refill at different steps (ragged step
     counts), the list ends with a single active slot, odd tile counts leave the last peer a dummy tile. inflight = 2 must
-    equal inflight = 1 and the single-CTA kernel bit for bit."""
+    equal inflight = 1, the round-1 pair kernel (v1, the engine default) and the single-CTA kernel bit for bit."""
     from fcl_taco2_b200.engine import Engine
     hp = hparams.preset(kind)
     sd = weights(kind, 0)
@@ -134,14 +134,15 @@ def test_decoder_two_super_tiles_in_flight(kind, max_pairs, n_rows):
     frame_off, ufo, order, totals = eng.len_reg_scan(d["dur"], d["utt_off"], pl.n_utts)
     F_ = int(pl.dur.sum())
     outs = {}
-    for name, pair, infl, mp in (("single", False, 1, None), ("pair1", True, 1, max_pairs), ("pair2", True, 2, max_pairs)):
-        eng.use_pair, eng.force_group, eng.pair_inflight, eng.max_pairs = pair, 1, infl, mp
+    for name, pair, kern, infl, mp in (("single", False, "v1", 1, None), ("v1", True, "v1", 1, max_pairs),
+                                       ("v2_1", True, "v2", 1, max_pairs), ("v2_2", True, "v2", 2, max_pairs)):
+        eng.use_pair, eng.force_group, eng.pair_kernel, eng.pair_inflight, eng.max_pairs = pair, 1, kern, infl, mp
         outs[name] = eng.decoder(hn, d["dur"], frame_off, order, d["row_utt"], d["row_phone"], F_, 0.1, 0.5, 31).clone()
-    eng.use_pair, eng.force_group, eng.pair_inflight, eng.max_pairs = None, 0, 1, None
+    eng.use_pair, eng.force_group, eng.pair_kernel, eng.pair_inflight, eng.max_pairs = None, 0, "v1", 2, None
     torch.cuda.synchronize()
-    assert torch.isfinite(outs["pair2"]).all()
-    assert torch.equal(outs["pair1"], outs["single"])
-    assert torch.equal(outs["pair2"], outs["single"]), float((outs["pair2"] - outs["single"]).abs().max())
+    assert torch.isfinite(outs["v2_2"]).all()
+    for name in ("v1", "v2_1", "v2_2"):
+        assert torch.equal(outs[name], outs["single"]), (name, float((outs[name] - outs["single"]).abs().max()))
 
 
 def test_t_batch32_group_mode_vs_oracle():
