@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 20
+ABI_VERSION = 21
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -156,7 +156,7 @@ ENTRY_POINTS = {
     "fcl_rows_to_image": RowsToImageParams,
     "fcl_conv_img_bf16": ConvImgParams,
 }
-PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_last_error", "fcl_sm_count", "fcl_struct_size",
+PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_operand_format", "fcl_last_error", "fcl_sm_count", "fcl_struct_size",
                  "fcl_decoder_bf16_workspace", "fcl_peer_alloc", "fcl_peer_free", "fcl_ipc_export", "fcl_ipc_open",
                  "fcl_ipc_close", "fcl_copy_async", "fcl_wait_flags", "fcl_write_flags"]
 
@@ -186,6 +186,7 @@ def load():
     lib.fcl_abi_version.restype = C.c_int
     lib.fcl_last_error.restype = C.c_char_p
     lib.fcl_sm_count.restype = C.c_int
+    lib.fcl_operand_format.restype = C.c_int
     lib.fcl_struct_size.restype = C.c_int
     lib.fcl_struct_size.argtypes = [C.c_int]
     if lib.fcl_abi_version() != ABI_VERSION:
@@ -227,6 +228,11 @@ def call(name: str, params, stream: int):
     rc = getattr(lib, name)(C.byref(params), C.c_void_p(stream))
     if rc != 0:
         raise FclError(f"{name} failed ({rc}): {lib.fcl_last_error().decode()}")
+
+
+def operand_format() -> str:
+    """'fp16' or 'bf16': element format of the 16-bit tensor-core operands this build of the library uses."""
+    return "bf16" if load().fcl_operand_format() == 1 else "fp16"
 
 
 def dptr(t):

@@ -39,17 +39,17 @@ __device__ __forceinline__ void load_gx16(const FclBiLstmBf16Params& p, long row
 #pragma unroll
     for (int k = 0; k < 4; ++k) { const float4 v = __ldg(s + k); g[4 * k] = v.x; g[4 * k + 1] = v.y; g[4 * k + 2] = v.z; g[4 * k + 3] = v.w; }
   } else {
-    const uint4* s = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.gx) + (size_t)row * (size_t)(8 * p.hidden) + col);
+    const uint4* s = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.gx) + (size_t)row * (size_t)(8 * p.hidden) + col);
     const uint4 a = __ldg(s), b = __ldg(s + 1);
     const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { g[2 * k] = __uint_as_float(w[k] << 16); g[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u); }
+    for (int k = 0; k < 8; ++k) { g[2 * k] = op_lo(w[k]); g[2 * k + 1] = op_hi(w[k]); }
   }
 }
 __device__ __forceinline__ void prefetch_gx16(const FclBiLstmBf16Params& p, long row, long prow, int col) {
   const void* a = p.gx_blk ? (p.gx_blk_half ? static_cast<const void*>(reinterpret_cast<const __half*>(p.gx_blk) + ((size_t)(col >> 4) * (size_t)p.gx_rows + (size_t)prow) * 16)
                                             : static_cast<const void*>(p.gx_blk + ((size_t)(col >> 4) * (size_t)p.gx_rows + (size_t)prow) * 16))
-                           : static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(p.gx) + (size_t)row * (size_t)(8 * p.hidden) + col);
+                           : static_cast<const void*>(reinterpret_cast<const uint16_t*>(p.gx) + (size_t)row * (size_t)(8 * p.hidden) + col);
   asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
 }
 
@@ -112,7 +112,7 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
     // ================================================================ MMA issuer
     if (elect_one()) {
       uint32_t stage = 0, sphase = 0, chunk_ctr = 0;
-      const uint32_t idesc = idesc_bf16_f32(128u, 256u);
+      const uint32_t idesc = idesc_op_f32(128u, 256u);
       for (int t = 0; t < steps; ++t) {
         mbar_wait(&sh.h_ready, (uint32_t)t & 1u);          // h(t-1) image complete (t = 0: zeros)
         tc_fence_after();
@@ -213,7 +213,7 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
             tc_fence_before();
             mbar_arrive(&sh.tmem_empty[buf]);
             ++chunk_ctr;
-            const uint2 hw = make_uint2(pack_bf16(hf[0], hf[1]), pack_bf16(hf[2], hf[3]));
+            const uint2 hw = make_uint2(pack_op(hf[0], hf[1]), pack_op(hf[2], hf[3]));
 #pragma unroll
             for (int k = 0; k < 4; ++k)                      // all four replicas of this utterance's row
               *reinterpret_cast<uint2*>(hnew + ((size_t)(ub >> 3) * 128 + k * 32 + lane) * 16 + (ub & 4) * 2) = hw;
@@ -275,8 +275,8 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) hf[g * 4 + j] = 0.f;
           }
-          hout[2 * g] = pack_bf16(hf[g * 4], hf[g * 4 + 1]);
-          hout[2 * g + 1] = pack_bf16(hf[g * 4 + 2], hf[g * 4 + 3]);
+          hout[2 * g] = pack_op(hf[g * 4], hf[g * 4 + 1]);
+          hout[2 * g + 1] = pack_op(hf[g * 4 + 2], hf[g * 4 + 3]);
         }
         tc_fence_before();
         mbar_arrive(&sh.tmem_empty[buf]);

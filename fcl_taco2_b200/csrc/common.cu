@@ -22,6 +22,13 @@ int check_launch(const char* what) {
 }  // namespace fcl
 
 extern "C" int fcl_abi_version(void) { return FCL_ABI_VERSION; }
+extern "C" int fcl_operand_format(void) {
+#ifdef FCL_OPERANDS_BF16
+  return 1;
+#else
+  return 0;
+#endif
+}
 extern "C" const char* fcl_last_error(void) { return fcl::g_err; }
 extern "C" int fcl_sm_count(void) {
   int dev = 0, n = 0;

@@ -196,7 +196,7 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     // ================================================================ MMA issuer (leader CTA only)
     if (rank == 0 && elect_one()) {
       uint32_t a_ctr = 0, b_ctr = 0, acc_ctr = 0;
-      const uint32_t idesc = idesc_bf16_f32(256u, (uint32_t)nb);
+      const uint32_t idesc = idesc_op_f32(256u, (uint32_t)nb);
       const uint32_t b_lbo = (uint32_t)(nb / 2) * 16u;
       for (int st = pair; st < n_super; st += n_pairs) {
         const uint32_t a_base = a_ctr;
@@ -296,8 +296,8 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
               v[4 * qd + 2] = act_t<ACT>(v[4 * qd + 2] + b.z); v[4 * qd + 3] = act_t<ACT>(v[4 * qd + 3] + b.w);
             }
             if constexpr (EPI == FCL_EPI_IMAGE) {
-              uint4 w0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-              uint4 w1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+              uint4 w0 = make_uint4(pack_op(v[0], v[1]), pack_op(v[2], v[3]), pack_op(v[4], v[5]), pack_op(v[6], v[7]));
+              uint4 w1 = make_uint4(pack_op(v[8], v[9]), pack_op(v[10], v[11]), pack_op(v[12], v[13]), pack_op(v[14], v[15]));
               if (!live) { w0 = zero4; w1 = zero4; }
               if (tile_ok) {
                 uint8_t* o = orow + (size_t)(c0 >> 3) * slab_stride;
@@ -412,8 +412,8 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                 dot = fmaf(v[4 * qd], hw.x, fmaf(v[4 * qd + 1], hw.y, fmaf(v[4 * qd + 2], hw.z, fmaf(v[4 * qd + 3], hw.w, dot))));
               }
             } else {
-              uint4 w0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-              uint4 w1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+              uint4 w0 = make_uint4(pack_op(v[0], v[1]), pack_op(v[2], v[3]), pack_op(v[4], v[5]), pack_op(v[6], v[7]));
+              uint4 w1 = make_uint4(pack_op(v[8], v[9]), pack_op(v[10], v[11]), pack_op(v[12], v[13]), pack_op(v[14], v[15]));
               if (!live) { w0 = zero4; w1 = zero4; }
               if (tile_ok) {
                 uint8_t* o = orow + (size_t)(c0 >> 3) * slab_stride;
@@ -491,12 +491,17 @@ rows_to_image_kernel(FclRowsToImageParams p) {
       const size_t row = p.gather ? (size_t)__ldg(p.gather + src) : (size_t)src;
       const float4* s = reinterpret_cast<const float4*>(p.src + row * p.ld + (size_t)slab * 8);
       const float4 a = __ldg(s), b = __ldg(s + 1);
-      w = make_uint4(umma::pack_bf16(a.x, a.y), umma::pack_bf16(a.z, a.w), umma::pack_bf16(b.x, b.y), umma::pack_bf16(b.z, b.w));
+      w = make_uint4(umma::pack_op(a.x, a.y), umma::pack_op(a.z, a.w), umma::pack_op(b.x, b.y), umma::pack_op(b.z, b.w));
     }
     reinterpret_cast<uint4*>(p.img)[i] = w;
   }
 }
 
+#ifdef FCL_OPERANDS_BF16
+constexpr CUtensorMapDataType kTmapDtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#else
+constexpr CUtensorMapDataType kTmapDtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#endif
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -567,7 +572,7 @@ extern "C" int fcl_conv_img_bf16(const FclConvImgParams* p, void* stream) {
     cuuint64_t dims[3] = {64, (cuuint64_t)(rows_alloc / 8), (cuuint64_t)(p->cin / 8)};
     cuuint64_t strides[2] = {128, (cuuint64_t)rows_alloc * 16};
     cuuint32_t box[3] = {64, 17, 8}, es[3] = {1, 1, 1};
-    CUresult r = enc(&amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p->in_img), dims, strides, box, es,
+    CUresult r = enc(&amap, kTmapDtype, 3, const_cast<void*>(p->in_img), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("fcl_conv_img_bf16: cuTensorMapEncodeTiled(input image) failed (%d)", (int)r); return FCL_ECUDA; }
@@ -578,7 +583,7 @@ extern "C" int fcl_conv_img_bf16(const FclConvImgParams* p, void* stream) {
     cuuint64_t dims[2] = {128, blocks * (cuuint64_t)(p->nb / 4)};
     cuuint64_t strides[1] = {256};
     cuuint32_t box[2] = {128, (cuuint32_t)(p->nb / 4)}, es[2] = {1, 1};
-    CUresult r = enc(&wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->w_packed), dims, strides, box, es,
+    CUresult r = enc(&wmap, kTmapDtype, 2, const_cast<void*>(p->w_packed), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("fcl_conv_img_bf16: cuTensorMapEncodeTiled(weights) failed (%d)", (int)r); return FCL_ECUDA; }

@@ -80,7 +80,7 @@ conv_stack_bf16_kernel(FclConvStackParams p, uint32_t img_bytes, uint32_t b_slot
             if (k0 + 16 * kg < cin) {
               const int slab = (k0 >> 3) + 2 * kg + (kq >> 1);
               *reinterpret_cast<uint2*>(img[0] + (size_t)slab * kCsSlab + (size_t)j * 16 + (kq & 1) * 8) =
-                  make_uint2(pack_bf16(v[kg].x, v[kg].y), pack_bf16(v[kg].z, v[kg].w));
+                  make_uint2(pack_op(v[kg].x, v[kg].y), pack_op(v[kg].z, v[kg].w));
             }
           }
         }
@@ -117,8 +117,8 @@ conv_stack_bf16_kernel(FclConvStackParams p, uint32_t img_bytes, uint32_t b_slot
 #pragma unroll
           for (int k8 = 0; k8 < 2; ++k8) {
             uint4 w;
-            w.x = pack_bf16(v[8 * k8], v[8 * k8 + 1]); w.y = pack_bf16(v[8 * k8 + 2], v[8 * k8 + 3]);
-            w.z = pack_bf16(v[8 * k8 + 4], v[8 * k8 + 5]); w.w = pack_bf16(v[8 * k8 + 6], v[8 * k8 + 7]);
+            w.x = pack_op(v[8 * k8], v[8 * k8 + 1]); w.y = pack_op(v[8 * k8 + 2], v[8 * k8 + 3]);
+            w.z = pack_op(v[8 * k8 + 4], v[8 * k8 + 5]); w.w = pack_op(v[8 * k8 + 6], v[8 * k8 + 7]);
             *reinterpret_cast<uint4*>(nxt + (size_t)((c0 >> 3) + k8) * kCsSlab) = w;
           }
         }
@@ -172,7 +172,7 @@ conv_stack_bf16_kernel(FclConvStackParams p, uint32_t img_bytes, uint32_t b_slot
       int it = 0;
       for (int l = 0; l < L; ++l) {
         const FclConvLayer& ly = p.layers[l];
-        const uint32_t idesc = idesc_bf16_f32(128u, (uint32_t)ly.cout);
+        const uint32_t idesc = idesc_op_f32(128u, (uint32_t)ly.cout);
         const uint32_t b_lbo = (uint32_t)ly.cout * 16u;
         const int kchunks = ly.cin / ly.kstage, ksteps = ly.kstage / 16, slabs = ly.kstage / 8;
         mbar_wait(&sh.img_ready[l], 0);            // also orders this layer after the previous epilogue's TMEM reads

@@ -195,8 +195,8 @@ __device__ __forceinline__ void prenet_store16(const float* v, const float* __re
       x[j] = u16 >= drop_thr ? y : 0.f;
     }
     uint4 w;
-    w.x = pack_bf16(x[0], x[1]); w.y = pack_bf16(x[2], x[3]);
-    w.z = pack_bf16(x[4], x[5]); w.w = pack_bf16(x[6], x[7]);
+    w.x = pack_op(x[0], x[1]); w.y = pack_op(x[2], x[3]);
+    w.z = pack_op(x[4], x[5]); w.w = pack_op(x[6], x[7]);
     *reinterpret_cast<uint4*>(dst + ((size_t)((col0 >> 3) + h8) * 128 + r) * 16) = w;
   }
 }
@@ -306,7 +306,7 @@ decoder_bf16_pair_kernel(FclDecoderBf16Params p) {
     if (elect_one()) {
       uint32_t stage = 0, sphase = 0;
       uint32_t chunk_ctr = 0;                          // accumulator buffer = chunk_ctr & 1
-      const uint32_t idesc_wide = idesc_bf16_f32(256u, 256u), idesc_feat = idesc_bf16_f32(256u, 128u);
+      const uint32_t idesc_wide = idesc_op_f32(256u, 256u), idesc_feat = idesc_op_f32(256u, 128u);
       // descriptors built incrementally (see decoder_bf16.cu): low word = (address >> 4) | (LBO >> 4) << 16
       const uint32_t ring_lo = smem_u32(smem) >> 4;
       constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
@@ -505,12 +505,12 @@ decoder_bf16_pair_kernel(FclDecoderBf16Params p) {
                   const float hn = og * tanh_fast(cn);
                   const uint4 zq = z_cur[ul >> 3];
                   const uint32_t zw = ((ul >> 1) & 3) == 0 ? zq.x : ((ul >> 1) & 3) == 1 ? zq.y : ((ul >> 1) & 3) == 2 ? zq.z : zq.w;
-                  const float zold = __uint_as_float((ul & 1) ? (zw & 0xFFFF0000u) : (zw << 16));
+                  const float zold = (ul & 1) ? op_hi(zw) : op_lo(zw);
                   zn[j] = fmaf(zo, zold, zk * hn);                      // decoder_sa.py:95-96 (eval blend)
                   cl[(size_t)u * 128 + r] = fmaf(zo, cold, zk * cn);
                 }
-                zout[2 * g] = pack_bf16(zn[0], zn[1]);
-                zout[2 * g + 1] = pack_bf16(zn[2], zn[3]);
+                zout[2 * g] = pack_op(zn[0], zn[1]);
+                zout[2 * g + 1] = pack_op(zn[2], zn[3]);
               }
               tc_fence_before();
               warp_arrive(&sh.tmem_empty[buf], lane);

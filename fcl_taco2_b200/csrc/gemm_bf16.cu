@@ -126,7 +126,7 @@ conv_gemm_bf16_kernel(FclConvGemmBf16Params p, int a_stages, int b_stages) {
             if (kg < kgroups) {
               const int slab = 2 * kg + (kq >> 1);      // k / 8 with k = 16 kg + 4 kq
               *reinterpret_cast<uint2*>(a_s + (size_t)slab * kSlabBytes + (size_t)jrow[i] * 16 + (kq & 1) * 8) =
-                  make_uint2(pack_bf16(v[i][kg].x, v[i][kg].y), pack_bf16(v[i][kg].z, v[i][kg].w));
+                  make_uint2(pack_op(v[i][kg].x, v[i][kg].y), pack_op(v[i][kg].z, v[i][kg].w));
             }
           }
         }
@@ -173,8 +173,8 @@ conv_gemm_bf16_kernel(FclConvGemmBf16Params p, int a_stages, int b_stages) {
               o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
             }
             if (p.out_bf16)
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)grow * p.ldo + n0 + c0 + col) =
-                  make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+              *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + (size_t)grow * p.ldo + n0 + c0 + col) =
+                  make_uint2(pack_op(o.x, o.y), pack_op(o.z, o.w));
             else
               *reinterpret_cast<float4*>(p.out + (size_t)grow * p.ldo + n0 + c0 + col) = o;
           }
@@ -199,7 +199,7 @@ conv_gemm_bf16_kernel(FclConvGemmBf16Params p, int a_stages, int b_stages) {
   } else {
     // ------------------------------------------------ MMA issuer
     if (elect_one()) {
-      const uint32_t idesc = idesc_bf16_f32(128u, (uint32_t)ntile);
+      const uint32_t idesc = idesc_op_f32(128u, (uint32_t)ntile);
       const uint32_t b_lbo = (uint32_t)ntile * 16u;
       int it = 0;
       for (int kc = 0; kc < kchunks; ++kc) {

@@ -6,6 +6,7 @@
 //                       (e2e_tts_tacotron2_sa.py:435-443,657-658; decoder_sa.py:570-571).
 // HBM-bound: one warp per row, float4 accesses.
 #include "common.cuh"
+#include "umma.cuh"
 #include <cuda_bf16.h>
 
 namespace fcl {
@@ -134,10 +135,7 @@ pack_rows_bf16_kernel(FclPackRowsParams p) {
     if (sidx < p.n_rows) {
       const float4* src = reinterpret_cast<const float4*>(p.src + (size_t)p.order[sidx] * p.ld + kc * 8);
       const float4 a = __ldg(src), b = __ldg(src + 1);
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
-      w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
-      w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+      w = make_uint4(umma::pack_op(a.x, a.y), umma::pack_op(a.z, a.w), umma::pack_op(b.x, b.y), umma::pack_op(b.z, b.w));
     }
     reinterpret_cast<uint4*>(p.dst)[i] = w;
   }

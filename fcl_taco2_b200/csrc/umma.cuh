@@ -10,8 +10,15 @@
 // descriptor start address by 2 * LBO. Weights are pre-packed in exactly this image in global memory
 // so a stage is ONE contiguous cp.async.bulk; activations are written in it by the producing threads
 // (a thread owns a row and stores 8 consecutive k as one 16-byte word: a warp writes 512 contiguous bytes).
+//
+// OPERAND FORMAT. The 16-bit GEMM operands are IEEE fp16 (11-bit significand) unless the library is built with
+// -DFCL_OPERANDS_BF16: kind::f16 MMAs run at the same rate for both, and fp16's rounding error is 8x smaller. Range is
+// not a concern on this path (BatchNorm / LayerNorm-normalised activations, LSTM states in [-1, 1], mel inputs of a few
+// units); every fp32 -> fp16 conversion SATURATES to +-65504 (cvt.rn.satfinite) instead of producing inf. The `_bf16`
+// suffix of the kernel / entry-point names is historical: it means "the 16-bit tensor-core path".
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace fcl {
@@ -83,9 +90,14 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-// instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, dense
-__host__ __device__ constexpr uint32_t idesc_bf16_f32(uint32_t m, uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+// instruction descriptor for kind::f16: D=f32, A=B=operand format (0 = fp16, 1 = bf16), both K-major, dense
+#ifdef FCL_OPERANDS_BF16
+constexpr uint32_t kOperandFormat = 1u;
+#else
+constexpr uint32_t kOperandFormat = 0u;
+#endif
+__host__ __device__ constexpr uint32_t idesc_op_f32(uint32_t m, uint32_t n) {
+  return (1u << 4) | (kOperandFormat << 7) | (kOperandFormat << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
@@ -133,9 +145,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // ---------------------------------------------------------------- small helpers
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+// two fp32 -> one 32-bit word of two operand elements (lo in bits 0-15), and back
+__device__ __forceinline__ uint32_t pack_op(float lo, float hi) {
+#ifdef FCL_OPERANDS_BF16
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+#else
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+#endif
+}
+__device__ __forceinline__ float op_lo(uint32_t w) {
+#ifdef FCL_OPERANDS_BF16
+  return __uint_as_float(w << 16);
+#else
+  return __low2float(*reinterpret_cast<const __half2*>(&w));
+#endif
+}
+__device__ __forceinline__ float op_hi(uint32_t w) {
+#ifdef FCL_OPERANDS_BF16
+  return __uint_as_float(w & 0xFFFF0000u);
+#else
+  return __high2float(*reinterpret_cast<const __half2*>(&w));
+#endif
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -124,7 +124,7 @@ def read_utts(json_path: str, pad_eos: bool = False):
     return ids, xs
 
 
-def build_model(idim, odim, train_args, test_teacher: bool, teacher_args=None, precision="bf16"):
+def build_model(idim, odim, train_args, test_teacher: bool, teacher_args=None, precision="fp16"):
     from .model import Tacotron2_sa, Tacotron2_sa_student
     com = argparse.Namespace(use_fe_condition=getattr(train_args, "use_fe_condition", True),
                              append_position=getattr(train_args, "append_position", True))
@@ -142,7 +142,7 @@ def decode(args, teacher_args=None):
     inference speeds (frames / s), the number the reference logs and writes to `<exp_name>.txt`."""
     idim, odim, train_args = get_model_conf(args.model, getattr(args, "model_conf", None))
     model = build_model(idim, odim, train_args, getattr(args, "test_teacher", True), teacher_args,
-                        getattr(args, "precision", "bf16"))
+                        getattr(args, "precision", "fp16"))
     logging.info("reading model parameters from " + args.model)
     load_weights(args.model, model)
     if getattr(args, "ngpu", 1) <= 0:
@@ -191,7 +191,7 @@ def get_parser():
     p.add_argument("--teacher-conf", type=str, default=None,
                    help="teacher YAML (conf/train_pytorch_tacotron2.sa.teacher.yaml) for the student's KD tensor shapes")
     p.add_argument("--batch-size", default=256, type=int)
-    p.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    p.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     p.add_argument("--verbose", "-V", default=0, type=int)
     # accepted for command-line compatibility; dead in the reference too (tts_decode.py:67-93, never read by inference())
     for dead, typ in (("--maxlenratio", float), ("--minlenratio", float), ("--threshold", float), ("--seed", int),

@@ -46,9 +46,12 @@ class Engine:
         """precision 'bf16': tcgen05 kernels. `bf16_gemms` (iterable of pack.GEMM_KEYS, default all) and
         `bf16_decoder` select which parts use them -- used by the error-budget diagnostics."""
         hp.validate()
-        if precision not in ("fp32", "bf16"):
+        if precision not in ("fp32", "fp16", "bf16"):
             raise ValueError(f"unknown precision {precision!r}")
-        self.hp, self.precision = hp, precision
+        # "fp16" = the 16-bit tensor-core path; "bf16" is its legacy alias. Which 16-bit operand format the kernels use
+        # is a build property of the library (fp16 by default: csrc/umma.cuh), reported as `operand_format`.
+        self.hp, self.precision = hp, ("fp32" if precision == "fp32" else "fp16")
+        self.operand_format = _lib.operand_format() if precision != "fp32" else "fp32"
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.FclError("the B200 path runs on CUDA devices only (no CPU fallback)")
@@ -61,8 +64,9 @@ class Engine:
     def _init_device_state(self, hp, packed, precision, bf16_gemms, bf16_decoder):
         self.w = {k: v.to(self.device) for k, v in packed.items()}
         self.wb = {}
-        if precision == "bf16":
+        if precision != "fp32":
             from . import pack as _pack
+            self.op_dtype = _pack.op_dtype()
             self.wb = {k: (t.to(self.device), nt, ks) for k, (t, nt, ks) in _pack.pack_bf16(packed).items()
                        if bf16_gemms is None or k in bf16_gemms}
             self.bf16_decoder = bf16_decoder
@@ -165,7 +169,7 @@ class Engine:
 
     def conv_tiles(self, seg_off, n_segs, max_tiles, halo=2):
         """Tile maps of a ragged row space for the tensor-core convolutions (None on the fp32 path)."""
-        if self.precision != "bf16":
+        if self.precision == "fp32":
             return None
         dev = self.device
         first = self._buf((n_segs + 1,), torch.int32)
@@ -195,7 +199,7 @@ class Engine:
         return {"n_tiles": n_tiles, "rows_alloc": n_tiles * 128 + 8, "prow_src": prow_src, "prow_off": prow_off}
 
     def rows_to_image(self, src, ld, chans, pad, gather=None, src_chans=0):
-        img = self._buf((chans // 8 * pad["rows_alloc"] * 8,), torch.bfloat16)
+        img = self._buf((chans // 8 * pad["rows_alloc"] * 8,), self.op_dtype)
         self._call("fcl_rows_to_image", _lib.RowsToImageParams(n_tiles=pad["n_tiles"], chans=chans, src=dptr(src), ld=ld,
                                                                gather=dptr(gather), prow_src=dptr(pad["prow_src"]),
                                                                img=dptr(img), src_chans=src_chans))
@@ -208,7 +212,7 @@ class Engine:
         wp, nb = weights if weights is not None else self.wi[key]
         out_img = out_blk = None
         if epi in (_lib.EPI_IMAGE, _lib.EPI_LN_IMAGE):
-            out_img = self._buf((cout // 8 * pad["rows_alloc"] * 8,), torch.bfloat16)
+            out_img = self._buf((cout // 8 * pad["rows_alloc"] * 8,), self.op_dtype)
         elif epi == _lib.EPI_BLOCKED_F32:
             out_blk = self._buf((cout // 16 * pad["n_tiles"] * 128 * 16,), torch.float32)
         elif epi == _lib.EPI_BLOCKED_F16:
@@ -239,7 +243,7 @@ class Engine:
             # write-back of this launch is what bounds it; bf16 here was the largest single rounding of the encoder
             gx = self.conv_img("blstm_wih", x, pad, hp.econv_chans, 4 * E, 1, ACT_NONE, _lib.EPI_BLOCKED_F16, bias=w["blstm_b"])
             return self._bilstm_bf16(None, utt_off, n_utts, P, gx_blk=gx, pad=pad)
-        if self.precision == "bf16" and self.use_encoder_stack and all(f"enc_conv{l}" in self.wb for l in range(3)):
+        if self.precision != "fp32" and self.use_encoder_stack and all(f"enc_conv{l}" in self.wb for l in range(3)):
             if lens is None:
                 lens = np.diff(utt_off.cpu().numpy().astype(np.int64))
             x = self.conv_stack([f"enc_conv{l}" for l in range(3)], [ACT_RELU] * 3, w["embed"], hp.embed_dim, P, utt_off,
@@ -261,8 +265,8 @@ class Engine:
         hp, w = self.hp, self.w
         E = hp.eunits
         h = self._buf((P, E), torch.float32)
-        if self.precision == "bf16" and getattr(self, "blstm_whh_bf16", None) is not None:
-            gx = self._buf((P, 4 * E), torch.bfloat16)
+        if self.precision != "fp32" and getattr(self, "blstm_whh_bf16", None) is not None:
+            gx = self._buf((P, 4 * E), self.op_dtype)
             self.conv_gemm(x, None, w["blstm_b"], P, hp.econv_chans, 4 * E, 1, ACT_NONE, key="blstm_wih", out=gx,
                            out_bf16=True)
             return self._bilstm_bf16(gx, utt_off, n_utts, P, h=h)
@@ -347,7 +351,7 @@ class Engine:
                 tile_rows=None, schedule=None):
         hp, w = self.hp, self.w
         P, E, H, O = hn.shape[0], hp.eunits, hp.dunits, hp.odim
-        if self.precision == "bf16" and self.bf16_decoder:
+        if self.precision != "fp32" and self.bf16_decoder:
             return self.decoder_bf16(hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p,
                                      dropout_seed, schedule)
         with self.stage("decoder_hoist"):
@@ -407,7 +411,7 @@ class Engine:
         P, E, H, O = hn.shape[0], hp.eunits, hp.dunits, hp.odim
         n_tiles = (P + 127) // 128
         with self.stage("decoder_hoist"):
-            hn_img = self._buf((n_tiles * 128 * E,), torch.bfloat16)
+            hn_img = self._buf((n_tiles * 128 * E,), self.op_dtype)
             self._call("fcl_pack_rows_bf16", _lib.PackRowsParams(n_rows=P, cols=E, src=dptr(hn), ld=E, order=dptr(order),
                                                                  dst=dptr(hn_img)))
         group, n_groups, n_slots, sched = schedule if schedule is not None else self.decoder_schedule(order, dur, P)
@@ -475,7 +479,7 @@ class Engine:
         consumer (the multi-GPU gather, a D2H copy) can start on finished frames while later chunks still compute."""
         hp, w = self.hp, self.w
         O, C = hp.odim, hp.postnet_chans
-        if self.precision == "bf16" and self.use_img_postnet and len(fseg) > 3 and n_frames > 0:
+        if self.precision != "fp32" and self.use_img_postnet and len(fseg) > 3 and n_frames > 0:
             # five image-to-image launches in the padded FRAME space (decoder_sa.py:274-286): the mel input is converted
             # once (80 -> 128 zero-padded channels), activations stay bf16 images, the last layer writes fp32 rows and
             # adds the residual (decoder_sa.py:632)
@@ -493,7 +497,7 @@ class Engine:
                 for k, (u0, u1, f0, f1) in enumerate(chunks):          # one launch sequence: hand everything over at the end
                     chunk_cb(k, final, f0, f1)
             return final
-        stack_ok = self.precision == "bf16" and len(fseg) > 3 and all(f"post_conv{l}" in self.wb for l in range(5))
+        stack_ok = self.precision != "fp32" and len(fseg) > 3 and all(f"post_conv{l}" in self.wb for l in range(5))
         if stack_ok and chunks and chunk_cb is not None:
             utt_frame_off, n_utts = fseg[3]
             final = torch.empty((n_frames, O), dtype=torch.float32, device=self.device)
@@ -626,7 +630,7 @@ class Engine:
             schedule. With forced durations it runs on a side stream concurrently with the encoder and predictors."""
             with self.stage("len_reg"):
                 frame_off, utt_frame_off, order, totals = self.len_reg_scan(dur, d["utt_off"], B)
-            sched = self.decoder_schedule(order, dur, P) if self.precision == "bf16" and self.bf16_decoder else None
+            sched = self.decoder_schedule(order, dur, P) if self.precision != "fp32" and self.bf16_decoder else None
             fmap = pos = ftiles = None
             if F is not None and need_fmap:
                 with self.stage("frame_map"):
@@ -636,7 +640,7 @@ class Engine:
 
         # the frame -> (row, step) map and the per-utterance frame tiles only serve the layer-by-layer / fused-stack postnet
         # (and the diagnostics of `extras`); the image postnet works from the frame offsets alone
-        need_fmap = extras or not (self.precision == "bf16" and self.use_img_postnet)
+        need_fmap = extras or not (self.precision != "fp32" and self.use_img_postnet)
         lr = None
         if not need_pred_dur:
             if not self.skip_zero_durations and (plan.dur == 0).any():
@@ -656,7 +660,7 @@ class Engine:
             else:
                 lr = length_regulation(d["dur"], F)
         with self.stage("encoder"):
-            if self.precision == "bf16" and self.use_img_convs and self.blstm_whh_bf16 is not None:
+            if self.precision != "fp32" and self.use_img_convs and self.blstm_whh_bf16 is not None:
                 seg = (d["seg_lo"], d["seg_hi"], None, self.pad_rows(d["utt_off"], B, P))
             else:
                 seg = (d["seg_lo"], d["seg_hi"], self.conv_tiles(d["utt_off"], B, int(((lens + 127) // 128).sum())))

@@ -15,6 +15,20 @@ from .hparams import HParams
 BN_EPS = 1e-5
 
 
+def op_dtype():
+    """torch dtype of the 16-bit tensor-core operands (weights are packed in the format the library was built for:
+    fp16 by default, bf16 with -DFCL_OPERANDS_BF16; csrc/umma.cuh)."""
+    from . import _lib
+    return torch.bfloat16 if _lib.operand_format() == "bf16" else torch.float16
+
+
+def _to_op(x: torch.Tensor) -> torch.Tensor:
+    dt = op_dtype()
+    if dt is torch.float16:
+        x = x.clamp(-65504.0, 65504.0)          # saturate like the kernels' conversions
+    return x.to(dt)
+
+
 def _interleave_gates(w: torch.Tensor, hidden: int) -> torch.Tensor:
     """(4H, K) rows [i;f;g;o] -> (K, 4H) with column u*4+g."""
     k = w.shape[1]
@@ -111,7 +125,7 @@ def pack_conv_bf16(w: torch.Tensor, ntile: int | None = None, kstage: int | None
     assert cout % ntile == 0 and cin % kstage == 0 and kstage % 16 == 0
     x = w.reshape(taps, cin // kstage, kstage // 8, 8, cout // ntile, ntile)      # t, kc, k8, j, nt, n
     x = x.permute(4, 1, 0, 2, 5, 3).contiguous()                                   # nt, kc, t, k8, n, j
-    return x.to(torch.bfloat16).reshape(-1).contiguous(), ntile, kstage
+    return _to_op(x).reshape(-1).contiguous(), ntile, kstage
 
 
 def choose_nb(cout: int) -> int:
@@ -131,7 +145,7 @@ def pack_conv_pair(w: torch.Tensor, nb: int | None = None):
     assert cin % 64 == 0 and cout % nb == 0 and nb % 64 == 0 and nb <= 256
     x = w.reshape(taps, cin // 64, 8, 8, cout // nb, 2, nb // 2)                   # t, kc, k8, j, blk, half, n
     x = x.permute(4, 1, 0, 5, 2, 6, 3).contiguous()                                 # blk, kc, t, half, k8, n, j
-    return x.to(torch.bfloat16).reshape(-1).contiguous(), nb
+    return _to_op(x).reshape(-1).contiguous(), nb
 
 
 IMG_KEYS = ["enc_conv0", "enc_conv1", "enc_conv2", "blstm_wih", "dur_conv0", "dur_conv1", "pitch_conv0", "pitch_conv1",

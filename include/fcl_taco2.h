@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 20
+#define FCL_ABI_VERSION 21
 
 enum {
   FCL_OK = 0,
@@ -39,6 +39,11 @@ enum {
 enum { FCL_ACT_NONE = 0, FCL_ACT_RELU = 1, FCL_ACT_TANH = 2 };
 
 int fcl_abi_version(void);
+/* Element format of the 16-bit GEMM operands (weights packed by the host, activation images written by the kernels) of
+ * every tensor-core entry point (the `_bf16` suffix of their names is historical): 0 = IEEE fp16 (default build: 11-bit
+ * significand, conversions saturate at +-65504), 1 = bfloat16 (library built with -DFCL_OPERANDS_BF16). The host packs
+ * weights in the format this returns. */
+int fcl_operand_format(void);
 const char* fcl_last_error(void);
 /* Number of SMs of the current device (grid sizing on the host side); <0 on error. */
 int fcl_sm_count(void);

@@ -16,8 +16,8 @@ pytestmark = pytest.mark.gpu
 
 def _ref_conv(a, w, bias, seg_lens, taps, act, residual):
     """a (rows,cin) fp32, w (taps,cin,cout) -> per-segment conv with zero halo, operands rounded to bf16."""
-    ab = a.to(torch.bfloat16).float()
-    wb = w.to(torch.bfloat16).float()
+    ab = a.to(pack.op_dtype()).float()
+    wb = w.to(pack.op_dtype()).float()
     outs, o = [], 0
     for n in seg_lens:
         x = ab[o:o + n].t().unsqueeze(0)                                   # (1,cin,n)
@@ -98,10 +98,10 @@ def test_conv_gemm_bf16_matches_bf16_rounded_reference(rows, cin, cout, taps, ac
 # ----------------------------------------------------------------------------- decoder / end-to-end, bf16 path
 # Stated tolerances of the tensor-core path (bf16 GEMM operands, fp32 accumulate, fp32 cell state,
 # tanh.approx activations) against the fp32 oracle, on mels of abs-mean ~1:
-DEC_MAX_ABS, DEC_MEAN_L1 = 2e-2, 3e-3       # decoder output before the postnet
-MEL_MAX_ABS, MEL_MEAN_L1 = 1.2e-1, 1.2e-2   # final mels, every GEMM in bf16 (observed <= 7.9e-2 / 8.2e-3 on the
-                                            # 500-phoneme stress case; tools/error_budget.py splits it by stage:
-                                            # the random-init postnet amplifies a 4.5e-3 decoder error ~6x)
+DEC_MAX_ABS, DEC_MEAN_L1 = 1e-2, 1.5e-3     # decoder output before the postnet
+MEL_MAX_ABS, MEL_MEAN_L1 = 3e-2, 4e-3       # final mels, every GEMM on the tensor cores with fp16 operands (observed
+                                            # <= 1.3e-2 / 1.2e-3 on S-1024, T-32 and the 500-phoneme stress batch; with
+                                            # bf16 operands -- round 1 -- the same path measured 8e-2 / 8.7e-3)
 
 from fcl_taco2_b200 import hparams, plan as planmod, synth          # noqa: E402
 from oracle import restate                                         # noqa: E402
@@ -118,7 +118,7 @@ def bf16_engines():
         if (kind, seed) not in out:
             hp = hparams.preset(kind)
             sd = weights(kind, seed)
-            out[(kind, seed)] = (Engine(hp, pack.pack_fp32(sd, hp), "cuda:0", "bf16"), sd, hp)
+            out[(kind, seed)] = (Engine(hp, pack.pack_fp32(sd, hp), "cuda:0", "fp16"), sd, hp)
         return out[(kind, seed)]
     return get
 
@@ -150,7 +150,7 @@ def test_decoder_bf16_steps(bf16_engines, kind, n_utts, drop):
 def test_e2e_bf16_against_reference_golden(name):
     from fcl_taco2_b200 import model as M
     g = load_golden(name)
-    m = M.from_preset(g["kind"], seed=None, device="cpu", precision="bf16")
+    m = M.from_preset(g["kind"], seed=None, device="cpu", precision="fp16")
     m.load_state_dict(weights(g["kind"], g["weight_seed"]))
     m = m.to("cuda:0").set_prenet_dropout(rate=g["dropout_rate"], seed=g["dropout_seed"])
     out = m.inference(torch.from_numpy(g["x"]), None, dur=g["dur"], dropout_utt_index=g["utt_index"])
@@ -161,7 +161,7 @@ def test_e2e_bf16_against_reference_golden(name):
 
 def test_bf16_batched_equals_looped():
     from fcl_taco2_b200 import model as M
-    m = M.from_preset("S", seed=3, device="cuda:0", precision="bf16").set_prenet_dropout(rate=0.5, seed=8)
+    m = M.from_preset("S", seed=3, device="cuda:0", precision="fp16").set_prenet_dropout(rate=0.5, seed=8)
     xs, ds = synth.synth_batch(5, 77)
     outs = m.inference_batch(xs, durs=ds)
     for i in range(len(xs)):
@@ -189,19 +189,19 @@ def test_fused_postnet_stack_matches_layer_by_layer(bf16_engines):
     torch.cuda.synchronize()
     assert torch.isfinite(img).all()
     mx_i, mean_i = err(img.cpu(), ref.cpu())
-    assert mx_i < 3e-2 and mean_i < 2e-3, (mx_i, mean_i)                    # same bf16 roundings, different summation order
+    assert mx_i < 6e-3 and mean_i < 4e-4, (mx_i, mean_i)                    # same bf16 roundings, different summation order
     for k in range(len(lens)):
         o = restate.postnet(sd, before[off[k]:off[k + 1]].cpu())
-        assert err(img[off[k]:off[k + 1]].cpu(), o)[0] < 8e-2
+        assert err(img[off[k]:off[k + 1]].cpu(), o)[0] < 2e-2
     assert torch.isfinite(fused).all()
     # The fused stack pads the first layer's K to 128 (different fp32 summation order): a handful of layer-0 outputs
     # round to the neighbouring bf16 value and each flip fans out over +-8 rows by the last layer (tools/dbg_stack.py:
     # both paths sit at the same distance from the fp32 oracle). Everything else is bit-identical.
     mx, mean = err(fused.cpu(), ref.cpu())
-    assert mx < 3e-2 and mean < 2e-3, (mx, mean)
+    assert mx < 6e-3 and mean < 4e-4, (mx, mean)
     for k in range(len(lens)):
         o = restate.postnet(sd, before[off[k]:off[k + 1]].cpu())
-        assert err(fused[off[k]:off[k + 1]].cpu(), o)[0] < 8e-2
+        assert err(fused[off[k]:off[k + 1]].cpu(), o)[0] < 2e-2
 
 
 def test_chunked_postnet_bit_identical(bf16_engines):
@@ -277,7 +277,7 @@ def test_bf16_predicted_durations_and_forced_prosody():
     from fcl_taco2_b200 import model as M
     sd = dict(weights("S", 2))
     sd["duration_predictor.linear.bias"] = torch.tensor([2.5])
-    m = M.from_preset("S", seed=None, device="cpu", precision="bf16")
+    m = M.from_preset("S", seed=None, device="cpu", precision="fp16")
     m.load_state_dict(sd)
     m = m.to("cuda:0").set_prenet_dropout(rate=0.5, seed=3)
     xs, _ = synth.synth_batch(5, 44)

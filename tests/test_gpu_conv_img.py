@@ -31,7 +31,7 @@ def _pad(lens):
 
 def _to_image(x, pd, gather=None, table=None):
     chans = (table if table is not None else x).shape[1]
-    img = torch.full((chans // 8 * pd["rows_alloc"] * 8,), float("nan"), dtype=torch.bfloat16, device="cuda")
+    img = torch.full((chans // 8 * pd["rows_alloc"] * 8,), float("nan"), dtype=pack.op_dtype(), device="cuda")
     src = (table if table is not None else x).cuda().contiguous()
     g = gather.cuda() if gather is not None else None
     _lib.call("fcl_rows_to_image", _lib.RowsToImageParams(n_tiles=pd["n_tiles"], chans=chans, src=dptr(src), ld=chans,
@@ -53,7 +53,7 @@ def _lens(total, rs, lo=1, hi=150):
 
 
 def _ref_conv(a, w, bias, lens, taps, relu=True):
-    ab, wb = a.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()
+    ab, wb = a.to(pack.op_dtype()).float(), w.to(pack.op_dtype()).float()
     outs, o = [], 0
     for n in lens:
         y = F.conv1d(ab[o:o + n].t().unsqueeze(0), wb.permute(2, 1, 0).contiguous(), bias, 1, taps // 2)[0].t()
@@ -79,12 +79,12 @@ def test_pad_rows_and_rows_to_image():
     assert (guard == 0).all()
     valid = torch.from_numpy(want >= 0)
     assert (rows[~valid] == 0).all()
-    assert torch.equal(rows[valid], x.to(torch.bfloat16).float())
+    assert torch.equal(rows[valid], x.to(pack.op_dtype()).float())
     # embedding gather
     table = torch.randn(76, 64, generator=torch.Generator().manual_seed(1))
     ids = torch.randint(0, 76, (pd["P"],), generator=torch.Generator().manual_seed(2))
     rows, _ = _image_rows(_to_image(None, pd, gather=ids, table=table), 64, pd)
-    assert torch.equal(rows[valid], table[ids].to(torch.bfloat16).float())
+    assert torch.equal(rows[valid], table[ids].to(pack.op_dtype()).float())
 
 
 @pytest.mark.parametrize("total,cin,cout,taps", [
@@ -107,7 +107,7 @@ def test_conv_img_image_epilogue(total, cin, cout, taps):
     wp, nb = pack.pack_conv_pair(w)
     wp, bias_d = wp.cuda(), bias.cuda()
     img = _to_image(a, pd)
-    out = torch.full((cout // 8 * pd["rows_alloc"] * 8,), float("nan"), dtype=torch.bfloat16, device="cuda")
+    out = torch.full((cout // 8 * pd["rows_alloc"] * 8,), float("nan"), dtype=pack.op_dtype(), device="cuda")
     _lib.call("fcl_conv_img_bf16", _lib.ConvImgParams(n_tiles=pd["n_tiles"], cin=cin, cout=cout, taps=taps, nb=nb,
                                                       act=_lib.ACT_RELU, epi=_lib.EPI_IMAGE, in_img=dptr(img), w_packed=dptr(wp),
                                                       bias=dptr(bias_d), prow_src=dptr(pd["prow_src"]), out_img=dptr(out)), _stream())
@@ -136,7 +136,7 @@ def test_conv_img_layernorm_epilogues(total, cin, C, head):
     wp, nb = pack.pack_conv_pair(w)
     dev = [t.cuda() for t in (wp, bias, gamma, beta, hw)]
     img = _to_image(a, pd)
-    out = torch.full((C // 8 * pd["rows_alloc"] * 8,), float("nan"), dtype=torch.bfloat16, device="cuda")
+    out = torch.full((C // 8 * pd["rows_alloc"] * 8,), float("nan"), dtype=pack.op_dtype(), device="cuda")
     head_out = torch.full((pd["P"],), float("nan"), device="cuda")
     dur_out = torch.full((pd["P"],), -1, dtype=torch.int32, device="cuda")
     _lib.call("fcl_conv_img_bf16", _lib.ConvImgParams(
@@ -182,7 +182,7 @@ def test_conv_img_blocked_epilogues(total, cin, cout, half):
     torch.cuda.synchronize()
     rows = out.float().view(cout // 16, R, 16).permute(1, 0, 2).reshape(R, cout).cpu()
     valid = (pd["prow_src"].cpu() >= 0)
-    ref = a.to(torch.bfloat16).float() @ w[0].to(torch.bfloat16).float() + bias
+    ref = a.to(pack.op_dtype()).float() @ w[0].to(pack.op_dtype()).float() + bias
     got = rows[valid]
     assert torch.isfinite(got).all()
     assert float((got - ref).abs().max()) < (3e-3 if half else 2e-3) * max(1.0, float(ref.abs().max()))

@@ -126,7 +126,7 @@ def test_inference_stream_matches_inference_batch():
     """The pipelined API (D2H of batch i overlapped with batch i+1) returns exactly what inference_batch returns,
     batch by batch, also when the batches differ in size (the pinned staging ring is reused and regrown)."""
     from fcl_taco2_b200 import model as M, synth
-    m = M.from_preset("S", seed=0, device="cuda:0", precision="bf16").set_prenet_dropout(rate=0.5, seed=3)
+    m = M.from_preset("S", seed=0, device="cuda:0", precision="fp16").set_prenet_dropout(rate=0.5, seed=3)
     sets = [synth.synth_batch(n, seed) for n, seed in ((5, 1), (9, 2), (3, 3), (12, 4), (1, 5))]
     want = []
     for k, (xs, ds) in enumerate(sets):
@@ -142,7 +142,7 @@ def test_inference_stream_matches_inference_batch():
     assert n == len(sets)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
 def test_zero_duration_phonemes_are_skipped(precision):
     """Extension: d = 0 phonemes feed the encoder / predictors / prosody embeddings but produce no
     decoder row and no frames, as in the reference's forward() (decoder_sa.py:459-463). Without the opt-in the call
@@ -161,7 +161,7 @@ def test_zero_duration_phonemes_are_skipped(precision):
         m.inference_batch(xs, durs=ds)
     outs = m.inference_batch(xs, durs=ds, skip_zero_durations=True)
     sd = weights("S", 4)
-    tol = (MAX_ABS, MEAN_L1) if precision == "fp32" else (1.2e-1, 1.2e-2)
+    tol = (MAX_ABS, MEAN_L1) if precision == "fp32" else (3e-2, 4e-3)
     for i in range(5):
         assert outs[i].shape == (int(ds[i].sum()), 80)
         if ds[i].sum() == 0:

@@ -26,7 +26,7 @@ pytestmark = pytest.mark.gpu
 
 def _model(kind, seed, drop_seed):
     from fcl_taco2_b200 import model as M
-    m = M.from_preset(kind, seed=None, device="cpu", precision="bf16")
+    m = M.from_preset(kind, seed=None, device="cpu", precision="fp16")
     m.load_state_dict(weights(kind, seed))
     return m.to("cuda:0").set_prenet_dropout(rate=0.5, seed=drop_seed)
 
@@ -75,7 +75,7 @@ def test_decoder_kernel_multi_tile_routes(kind, n_rows):
     from fcl_taco2_b200.engine import Engine
     hp = hparams.preset(kind)
     sd = weights(kind, 0)
-    eng = Engine(hp, pack.pack_fp32(sd, hp), "cuda:0", "bf16")
+    eng = Engine(hp, pack.pack_fp32(sd, hp), "cuda:0", "fp16")
     rs = np.random.RandomState(3)
     lens = []
     while sum(lens) < n_rows:
@@ -121,7 +121,7 @@ def test_decoder_two_super_tiles_in_flight(kind, max_pairs, n_rows):
     from fcl_taco2_b200.engine import Engine
     hp = hparams.preset(kind)
     sd = weights(kind, 0)
-    eng = Engine(hp, pack.pack_fp32(sd, hp), "cuda:0", "bf16")
+    eng = Engine(hp, pack.pack_fp32(sd, hp), "cuda:0", "fp16")
     rs = np.random.RandomState(n_rows)
     lens = []
     while sum(lens) < n_rows:
@@ -187,7 +187,7 @@ def test_bilstm_bf16_kernel_many_tiles(kind, n_utts, tile_utts):
     P = int(off[-1])
     x = torch.randn(P, hp.econv_chans, generator=torch.Generator().manual_seed(1))
     # gate-interleaved input projection, rounded to bf16 (the kernel's gx operand)
-    gx = (x @ packed["blstm_wih"][0] + packed["blstm_b"]).to(torch.bfloat16)
+    gx = (x @ packed["blstm_wih"][0] + packed["blstm_b"]).to(pack.op_dtype())
     whh = pack.pack_bilstm_whh_bf16(packed).cuda()
     n_tiles = (n_utts + tile_utts - 1) // tile_utts
     assert n_tiles > 64 or kind == "T"

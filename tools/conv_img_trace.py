@@ -20,9 +20,9 @@ w = torch.randn(taps, cin, cout, generator=g) / np.sqrt(cin * taps)
 wp, nb = pack.pack_conv_pair(w, force_nb)
 wp = wp.cuda()
 rows_alloc = tiles * 128 + 8
-img = (torch.randn(cin // 8 * rows_alloc * 8, generator=g) * 0.5).to(torch.bfloat16).cuda()
+img = (torch.randn(cin // 8 * rows_alloc * 8, generator=g) * 0.5).to(pack.op_dtype()).cuda()
 prow_src = torch.arange(tiles * 128, dtype=torch.int32).cuda()
-out_img = torch.empty(cout // 8 * rows_alloc * 8, dtype=torch.bfloat16, device="cuda")
+out_img = torch.empty(cout // 8 * rows_alloc * 8, dtype=pack.op_dtype(), device="cuda")
 out_blk = torch.empty(cout // 16 * tiles * 128 * 16, dtype=torch.float16, device="cuda")
 vec = lambda: torch.randn(cout, generator=g).cuda()
 bias, gamma, beta, hw = vec(), vec(), vec(), vec()

@@ -4,7 +4,7 @@ from fcl_taco2_b200 import hparams, pack
 from fcl_taco2_b200.engine import Engine
 from tests.helpers import weights
 hp = hparams.preset("S"); sd = weights("S", 0)
-eng = Engine(hp, pack.pack_fp32(sd, hp), "cuda:0", "bf16")
+eng = Engine(hp, pack.pack_fp32(sd, hp), "cuda:0", "fp16")
 lens = [300, 5, 1, 112, 113, 64, 700]
 F_ = sum(lens)
 before = torch.randn(F_, 80, generator=torch.Generator().manual_seed(1)).cuda()

@@ -7,7 +7,7 @@ from fcl_taco2_b200 import model as M, synth, plan as planmod
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "S"
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
-m = M.from_preset(kind, seed=0, device="cuda:0", precision="bf16").set_prenet_dropout(rate=0.5, seed=1)
+m = M.from_preset(kind, seed=0, device="cuda:0", precision="fp16").set_prenet_dropout(rate=0.5, seed=1)
 eng = m.engine()
 eng.use_pair = len(sys.argv) > 3 and sys.argv[3] == "pair"
 NLINES = int(sys.argv[4]) if len(sys.argv) > 4 else 140

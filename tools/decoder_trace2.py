@@ -10,7 +10,7 @@ kind = sys.argv[1] if len(sys.argv) > 1 else "S"
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 infl = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 NLINES = int(sys.argv[4]) if len(sys.argv) > 4 else 120
-m = M.from_preset(kind, seed=0, device="cuda:0", precision="bf16").set_prenet_dropout(rate=0.5, seed=1)
+m = M.from_preset(kind, seed=0, device="cuda:0", precision="fp16").set_prenet_dropout(rate=0.5, seed=1)
 eng = m.engine()
 eng.use_pair, eng.pair_inflight = True, infl
 xs, ds = synth.synth_batch(batch, 0)

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(640, 1) rate_kernel(Cfg c, const uint8_t* __re
 
   if (warp == 1 && c.mma_stages > 0 && rank == 0) {
     if (elect_one()) {
-      const uint32_t idesc = idesc_bf16_f32(PAIR ? 256u : 128u, 256u);
+      const uint32_t idesc = idesc_op_f32(PAIR ? 256u : 128u, 256u);
       const uint32_t b_rows = PAIR ? 128u : 256u;      // rows of B held by THIS CTA
       const long long t0 = clock64();
       const int group = 16;                              // commit every 16 stages, wait one group behind
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(128, 1) stream_kernel(int n_stages, int ring, 
     __syncwarp();
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc = idesc_bf16_f32(PAIR ? 256u : 128u, 256u);
+      const uint32_t idesc = idesc_op_f32(PAIR ? 256u : 128u, 256u);
       const uint32_t b_rows = (uint32_t)b_bytes / 128u;
       uint32_t stage = 0, ph = 0;
       const long long t0 = clock64();
