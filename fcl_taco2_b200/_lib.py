@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 21
+ABI_VERSION = 22
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -84,7 +84,7 @@ class DecoderParams(C.Structure):
                 ("order", ptr), ("dur", ptr), ("frame_off", ptr), ("row_utt", ptr), ("row_phone", ptr),
                 ("g0h", ptr), ("y0h", ptr), ("wp0", ptr), ("bp0", ptr), ("wp1", ptr), ("bp1", ptr),
                 ("w0", ptr), ("wpos", ptr), ("w1", ptr), ("b1", ptr), ("wf", ptr), ("cstate", ptr), ("before", ptr),
-                ("zoneout", f32), ("dropout_p", f32), ("dropout_seed", u64), ("tile_rows", i32)]
+                ("zoneout", f32), ("dropout_p", f32), ("dropout_seed", u64), ("tile_rows", i32), ("tf_y", ptr)]
 
 
 class DecoderBf16Params(C.Structure):
@@ -94,13 +94,19 @@ class DecoderBf16Params(C.Structure):
                 ("wpos", ptr), ("b0", ptr), ("b1", ptr), ("group", i32), ("act_priv", ptr), ("act_shared", ptr),
                 ("c_ws", ptr), ("group_sync", ptr), ("before", ptr),
                 ("zoneout", f32), ("dropout_p", f32), ("dropout_seed", u64), ("tile_slot", ptr), ("tile_rank", ptr),
-                ("trace", ptr), ("trace_cap", i32), ("inflight", i32)]
+                ("trace", ptr), ("trace_cap", i32), ("inflight", i32), ("tf_x1", ptr)]
 
 
 class BiLstmBf16Params(C.Structure):
     _fields_ = [("n_utts", i32), ("hidden", i32), ("tile_utts", i32), ("utt_off", ptr), ("gx", ptr),
                 ("whh_packed", ptr), ("c_ws", ptr), ("out", ptr), ("gx_blk", ptr), ("prow_off", ptr), ("gx_rows", i32),
                 ("gx_blk_half", i32)]
+
+
+class Prenet0TfParams(C.Structure):
+    _fields_ = [("n_frames", i32), ("odim", i32), ("prenet_units", i32), ("y", ptr), ("frame_row", ptr), ("frame_step", ptr),
+                ("row_utt", ptr), ("row_phone", ptr), ("wp0", ptr), ("bp0", ptr), ("dropout_p", f32), ("dropout_seed", u64),
+                ("x1", ptr)]
 
 
 class PadRowsParams(C.Structure):
@@ -132,7 +138,7 @@ class PackRowsParams(C.Structure):
 
 STRUCTS = [LenRegParams, FrameMapParams, ConvGemmParams, LayerNormParams, EmbedAddParams, BiLstmParams,
            DecoderParams, ConvGemmBf16Params, DecoderBf16Params, PackRowsParams, BiLstmBf16Params, ConvTilesParams, DecoderScheduleParams, ConvStackTilesParams,
-           ConvStackParams, PadRowsParams, RowsToImageParams, ConvImgParams]
+           ConvStackParams, PadRowsParams, RowsToImageParams, ConvImgParams, Prenet0TfParams]
 
 ENTRY_POINTS = {
     "fcl_len_reg_scan": LenRegParams,
@@ -155,6 +161,7 @@ ENTRY_POINTS = {
     "fcl_pad_rows": PadRowsParams,
     "fcl_rows_to_image": RowsToImageParams,
     "fcl_conv_img_bf16": ConvImgParams,
+    "fcl_prenet0_tf": Prenet0TfParams,
 }
 PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_operand_format", "fcl_last_error", "fcl_sm_count", "fcl_struct_size",
                  "fcl_decoder_bf16_workspace", "fcl_peer_alloc", "fcl_peer_free", "fcl_ipc_export", "fcl_ipc_open",

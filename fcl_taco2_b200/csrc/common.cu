@@ -61,6 +61,7 @@ extern "C" int fcl_struct_size(int which) {
     case 15: return (int)sizeof(FclPadRowsParams);
     case 16: return (int)sizeof(FclRowsToImageParams);
     case 17: return (int)sizeof(FclConvImgParams);
+    case 18: return (int)sizeof(FclPrenet0TfParams);
     default: return -1;
   }
 }

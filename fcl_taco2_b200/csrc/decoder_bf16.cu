@@ -200,7 +200,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
           const uint8_t* z1cur = zsh + db_z_off(H, zset, 2 + zp), *z1new = zsh + db_z_off(H, zset, 2 + (zp ^ 1));
           for (int phase = 0; phase < 4; ++phase) {
             if (tid == 0) db_trace(p, 600 + phase);
-            const int nch = dm.nchunks(phase, m + 1 == steps), kst = dm.kstages(phase), late = dm.late_stage(phase);
+            const int nch = dm.nchunks(phase, m + 1 == steps || p.tf_x1 != nullptr), kst = dm.kstages(phase), late = dm.late_stage(phase);
             bool waited = false;
             if (dm.C > 1 && phase >= 2) {
               // group mode: tell the other CTAs of the tile that this CTA's slice of z0' (z1') is written
@@ -270,7 +270,7 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
         const int steps = min(max(p.dur[p.order[(size_t)tile * 128]], 0), FCL_MAX_DURATION);
         for (int m = 0; m < steps; ++m) {
           for (int phase = 0; phase < 4; ++phase) {
-            const int nch = dm.nchunks(phase, m + 1 == steps), kst = dm.kstages(phase);
+            const int nch = dm.nchunks(phase, m + 1 == steps || p.tf_x1 != nullptr), kst = dm.kstages(phase);
             for (int c = 0; c < nch; ++c) {
               if (!dm.owns(phase, c)) continue;
               const bool feat = phase == 3 && c == 0;
@@ -461,8 +461,20 @@ decoder_bf16_kernel(FclDecoderBf16Params p) {
           ++chunk_ctr;
           if (tid == 128) db_trace(p, 530);
         }
+        // ---------------- teacher forcing: the next step's x1 image comes from the ground-truth frame (fcl_prenet0_tf)
+        if (p.tf_x1 && m + 1 < steps) {
+          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.tf_x1) + ((size_t)foff + m) * U + cs * 64);
+          const bool live = row >= 0 && m + 1 < d;
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8) {
+            const uint4 w = live ? __ldg(src + k8) : make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(act + db_x1_off() + ((size_t)(cs * 8 + k8) * 128 + r) * 16) = w;
+          }
+          fence_proxy_async_global();
+          warp_arrive(&sh.a_ready[0], lane);
+        }
         // ---------------- FP chunk 1: prenet layer 0 of the NEXT step (composed with feat_out) -> x1 image
-        if (m + 1 < steps) {
+        if (m + 1 < steps && !p.tf_x1) {
           const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
           mbar_wait(&sh.tmem_full[buf], use & 1u);
           tc_fence_after();

@@ -594,6 +594,7 @@ extern "C" int fcl_decoder_bf16_pair(const FclDecoderBf16Params* p, void* stream
   FCL_REQUIRE(p->n_slots >= 2 && p->n_slots % 2 == 0, "n_slots must be even (CTA pairs)");
   FCL_REQUIRE(p->zoneout >= 0.f && p->zoneout < 1.f && p->dropout_p >= 0.f && p->dropout_p < 1.f, "bad rates");
   FCL_REQUIRE((long long)((p->n_tiles + 1) / 2) <= (long long)kDbMaxTilesPerCta * (p->n_slots / 2), "too many tiles");
+  FCL_REQUIRE(!p->tf_x1, "teacher forcing is implemented in fcl_decoder_bf16 and fcl_decoder_bf16_pair_v1");
   const size_t smem = (size_t)kDbStages * kStageBytes;
   if (int rc = ensure_dyn_smem(decoder_bf16_pair_kernel, smem, "fcl_decoder_bf16_pair")) return rc;
   cudaLaunchConfig_t cfg = {};

@@ -204,9 +204,15 @@ decoder_f32_kernel(FclDecoderParams p) {
       fma_panel(acc, z1_s + r0, LD, p.wf + col, O, H);
 #pragma unroll
       for (int i = 0; i < RT; ++i) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) x0_s[(col + j) * LD + r0 + i] = acc[i][j];
-        if (m_row[r0 + i] >= 0 && m < m_dur[r0 + i])                 // exhausted rows are masked (decoder_sa.py:625-629)
+        const bool live = m_row[r0 + i] >= 0 && m < m_dur[r0 + i];
+        float4 nxt = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);      // next step's prenet input
+        if (p.tf_y) {                                                 // teacher forcing: prev_out = y (decoder_sa.py:510)
+          nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live) nxt = __ldg(reinterpret_cast<const float4*>(p.tf_y + ((size_t)m_foff[r0 + i] + m) * O + col));
+        }
+        x0_s[(col + 0) * LD + r0 + i] = nxt.x; x0_s[(col + 1) * LD + r0 + i] = nxt.y;
+        x0_s[(col + 2) * LD + r0 + i] = nxt.z; x0_s[(col + 3) * LD + r0 + i] = nxt.w;
+        if (live)                                                     // exhausted rows are masked (decoder_sa.py:625-629)
           *reinterpret_cast<float4*>(p.before + ((size_t)m_foff[r0 + i] + m) * O + col) =
               make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       }

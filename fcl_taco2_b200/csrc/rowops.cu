@@ -141,7 +141,60 @@ pack_rows_bf16_kernel(FclPackRowsParams p) {
   }
 }
 
+// prenet.0 of ground-truth frames for the teacher-forced decoder: one thread = (frame, 8 units). The 80 x 256 weight
+// is read through L1 (every thread of a warp reads the same k, consecutive units).
+__global__ void __launch_bounds__(256)
+prenet0_tf_kernel(FclPrenet0TfParams p) {
+  const int U = p.prenet_units, O = p.odim, u8 = U >> 3;
+  const size_t total = (size_t)p.n_frames * u8;
+  const bool use_drop = p.dropout_p > 0.f;
+  const uint32_t thr = dropout_threshold16(p.dropout_p);
+  const float scale = use_drop ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i / u8), oct = (int)(i - (size_t)f * u8);
+    float acc[8];
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bp0 + 8 * oct)), b1 = __ldg(reinterpret_cast<const float4*>(p.bp0 + 8 * oct) + 1);
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    const float* yr = p.y + (size_t)f * O;
+    for (int k = 0; k < O; ++k) {
+      const float yv = __ldg(yr + k);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.wp0 + (size_t)k * U + 8 * oct));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.wp0 + (size_t)k * U + 8 * oct) + 1);
+      acc[0] = fmaf(yv, w0.x, acc[0]); acc[1] = fmaf(yv, w0.y, acc[1]); acc[2] = fmaf(yv, w0.z, acc[2]); acc[3] = fmaf(yv, w0.w, acc[3]);
+      acc[4] = fmaf(yv, w1.x, acc[4]); acc[5] = fmaf(yv, w1.y, acc[5]); acc[6] = fmaf(yv, w1.z, acc[6]); acc[7] = fmaf(yv, w1.w, acc[7]);
+    }
+    Philox4 rnd = Philox4{0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (use_drop) {
+      const int row = __ldg(p.frame_row + f);
+      rnd = dropout_words(p.dropout_seed, (uint32_t)__ldg(p.row_utt + row), (uint32_t)__ldg(p.row_phone + row),
+                          (uint32_t)(__ldg(p.frame_step + f) + 1), 0u, (uint32_t)oct);
+    }
+    const uint32_t wv[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t u16 = (j & 1) ? (wv[j >> 1] >> 16) : (wv[j >> 1] & 0xFFFFu);
+      const float v = fmaxf(acc[j], 0.f) * scale;
+      x[j] = u16 >= thr ? v : 0.f;
+    }
+    reinterpret_cast<uint4*>(p.x1)[i] = make_uint4(umma::pack_op(x[0], x[1]), umma::pack_op(x[2], x[3]), umma::pack_op(x[4], x[5]),
+                                                   umma::pack_op(x[6], x[7]));
+  }
+}
+
 }  // namespace fcl
+
+extern "C" int fcl_prenet0_tf(const FclPrenet0TfParams* p, void* stream) {
+  using namespace fcl;
+  FCL_REQUIRE(p && p->y && p->frame_row && p->frame_step && p->row_utt && p->row_phone && p->wp0 && p->bp0 && p->x1, "null pointer");
+  FCL_REQUIRE(p->n_frames > 0 && p->odim > 0 && p->prenet_units % 8 == 0 && p->dropout_p >= 0.f && p->dropout_p < 1.f, "bad sizes");
+  int sms = fcl_sm_count();
+  if (sms < 0) return sms;
+  const size_t total = (size_t)p->n_frames * (p->prenet_units / 8);
+  const size_t blocks = (total + 255) / 256;
+  prenet0_tf_kernel<<<(unsigned)(blocks < (size_t)sms * 16 ? blocks : (size_t)sms * 16), 256, 0, as_stream(stream)>>>(*p);
+  return check_launch("fcl_prenet0_tf");
+}
 
 extern "C" int fcl_pack_rows_bf16(const FclPackRowsParams* p, void* stream) {
   using namespace fcl;

@@ -348,12 +348,21 @@ class Engine:
         return buf, pos
 
     def decoder(self, hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p, dropout_seed,
-                tile_rows=None, schedule=None):
+                tile_rows=None, schedule=None, tf=None):
+        """`tf` = (ys (F, O) fp32 ground-truth frames in output order, frame_row, frame_step): teacher forcing."""
         hp, w = self.hp, self.w
         P, E, H, O = hn.shape[0], hp.eunits, hp.dunits, hp.odim
         if self.precision != "fp32" and self.bf16_decoder:
+            tf_x1 = None
+            if tf is not None:
+                # prenet.0 of the ground-truth frames for all steps at once (it does not depend on the recurrence)
+                tf_x1 = self._buf((max(n_frames, 1), hp.prenet_units), self.op_dtype)
+                self._call("fcl_prenet0_tf", _lib.Prenet0TfParams(
+                    n_frames=n_frames, odim=O, prenet_units=hp.prenet_units, y=dptr(tf[0]), frame_row=dptr(tf[1]),
+                    frame_step=dptr(tf[2]), row_utt=dptr(row_utt), row_phone=dptr(row_phone), wp0=dptr(w["dec_wp0"]),
+                    bp0=dptr(w["dec_bp0"]), dropout_p=dropout_p, dropout_seed=dropout_seed, x1=dptr(tf_x1)))
             return self.decoder_bf16(hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p,
-                                     dropout_seed, schedule)
+                                     dropout_seed, schedule, tf_x1=tf_x1)
         with self.stage("decoder_hoist"):
             g0h = self.conv_gemm(hn, w["dec_g0h_w"], w["dec_g0h_b"], P, E, 4 * H, 1, ACT_NONE)
             y0h = self.conv_gemm(hn, w["dec_y0h_w"], None, P, E, O, 1, ACT_NONE)
@@ -367,7 +376,7 @@ class Engine:
                                wp1=dptr(w["dec_wp1"]), bp1=dptr(w["dec_bp1"]), w0=dptr(w["dec_w0"]),
                                wpos=dptr(w["dec_wpos"]), w1=dptr(w["dec_w1"]), b1=dptr(w["dec_b1"]), wf=dptr(w["dec_wf"]),
                                cstate=dptr(cstate), before=dptr(before), zoneout=zoneout, dropout_p=dropout_p,
-                               dropout_seed=dropout_seed, tile_rows=tile_rows)
+                               dropout_seed=dropout_seed, tile_rows=tile_rows, tf_y=dptr(tf[0]) if tf is not None else None)
         with self.stage("decoder_loop"):
             self._call("fcl_decoder_f32", p)
         return before
@@ -404,7 +413,7 @@ class Engine:
         return group, n_groups, n_slots, sched
 
     def decoder_bf16(self, hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p, dropout_seed,
-                     schedule=None):
+                     schedule=None, tf_x1=None):
         """Tensor-core decoder: h packed as a bf16 operand image in duration-sorted tile order, then the
         persistent tcgen05 loop."""
         hp, w = self.hp, self.w
@@ -429,10 +438,10 @@ class Engine:
                                    dropout_p=dropout_p, dropout_seed=dropout_seed, tile_slot=dptr(sched[0]),
                                    tile_rank=dptr(sched[1]), trace=dptr(trace),
                                    trace_cap=(trace.numel() - 2) // 2 if trace is not None else 0,
-                                   inflight=self.pair_inflight)
+                                   inflight=self.pair_inflight, tf_x1=dptr(tf_x1))
         with self.stage("decoder_loop"):
-            self._call(("fcl_decoder_bf16_pair_v1" if self.pair_kernel == "v1" else "fcl_decoder_bf16_pair") if group < 0
-                       else "fcl_decoder_bf16", p)
+            self._call(("fcl_decoder_bf16_pair_v1" if (self.pair_kernel == "v1" or tf_x1 is not None) else "fcl_decoder_bf16_pair")
+                       if group < 0 else "fcl_decoder_bf16", p)
         return before
 
     def conv_stack(self, keys, acts, x, ld_in, rows, seg_off, n_segs, max_len_sum_tiles, taps=5, gather=None,
@@ -596,24 +605,29 @@ class Engine:
 
     @torch.no_grad()
     def run(self, plan: BatchPlan, zoneout: float, dropout_p: float, dropout_seed: int,
-            extras: bool = False, tile_rows=None) -> BatchResult:
+            extras: bool = False, tile_rows=None, tf_y=None) -> BatchResult:
+        """`tf_y` (F, odim) fp32 on the device, frames of all utterances in PROCESSING order: teacher-forced pass
+        (the reference's forward(): decoder_sa.py:431-542); the predictors' outputs come back in `extras`."""
         with torch.cuda.device(self.device):
             d, h2d = self.upload(plan)
-            return self.run_uploaded(plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d)
+            return self.run_uploaded(plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d, tf_y=tf_y)
 
     @torch.no_grad()
     def run_uploaded(self, plan: BatchPlan, d: dict, zoneout: float, dropout_p: float, dropout_seed: int,
-                     extras: bool = False, tile_rows=None, h2d: int = 0, out_chunks: int = 0, chunk_cb=None) -> BatchResult:
+                     extras: bool = False, tile_rows=None, h2d: int = 0, out_chunks: int = 0, chunk_cb=None,
+                     tf_y=None) -> BatchResult:
         """The pass proper, inputs already resident on the device (`d` from `upload`)."""
         self._arena_seq, self._in_pass = 0, not extras     # extras (tests) keep intermediates: no recycling
         try:
             with torch.cuda.device(self.device):           # launches go to the engine's device whatever is current outside
-                return self._run_uploaded(plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d, out_chunks, chunk_cb)
+                return self._run_uploaded(plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d, out_chunks, chunk_cb,
+                                          tf_y)
         finally:
             self._in_pass = False
             self._stream_handle = None
 
-    def _run_uploaded(self, plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d, out_chunks=0, chunk_cb=None):
+    def _run_uploaded(self, plan, d, zoneout, dropout_p, dropout_seed, extras, tile_rows, h2d, out_chunks=0, chunk_cb=None,
+                      tf_y=None):
         hp = self.hp
         B, P = plan.n_utts, plan.n_rows
         ex = {"h2d_bytes": h2d}
@@ -640,7 +654,9 @@ class Engine:
 
         # the frame -> (row, step) map and the per-utterance frame tiles only serve the layer-by-layer / fused-stack postnet
         # (and the diagnostics of `extras`); the image postnet works from the frame offsets alone
-        need_fmap = extras or not (self.precision != "fp32" and self.use_img_postnet)
+        need_fmap = extras or tf_y is not None or not (self.precision != "fp32" and self.use_img_postnet)
+        if tf_y is not None and need_pred_dur:
+            raise ValueError("teacher forcing needs the ground-truth durations (forward(): extras / ds)")
         lr = None
         if not need_pred_dur:
             if not self.skip_zero_durations and (plan.dur == 0).any():
@@ -667,12 +683,15 @@ class Engine:
             h = self.encoder(d["ids"], d["utt_off"], seg, B, lens=lens)
         dlog = dur_pred = None
         with self.stage("predictors"):
-            if need_pred_dur or extras:
+            if need_pred_dur or extras or tf_y is not None:
                 dlog, dur_pred = self.predictor("dur", h, seg, want_dur=True)
             dur = dur_pred if need_pred_dur else d["dur"]
+            pitch_pred = energy_pred = None
+            if plan.pitch is None or tf_y is not None:
+                pitch_pred, _ = self.predictor("pitch", h, seg)
+                energy_pred, _ = self.predictor("energy", h, seg)
             if plan.pitch is None:
-                pitch, _ = self.predictor("pitch", h, seg)
-                energy, _ = self.predictor("energy", h, seg)
+                pitch, energy = pitch_pred, energy_pred
             else:
                 pitch, energy = d["pitch"], d["energy"]
             hn = self.embed_add(h, pitch, energy, seg)
@@ -697,12 +716,17 @@ class Engine:
             frame_off, utt_frame_off, order, totals, sched, fmap, pos, ftiles = lr
             if use_side:
                 main.wait_stream(side)
+        if tf_y is not None and tuple(tf_y.shape) != (F, hp.odim):
+            raise ValueError(f"teacher forcing: {tuple(tf_y.shape)} target frames for {F} frames of duration")
         before = self.decoder(hn, dur, frame_off, order, d["row_utt"], d["row_phone"], F, zoneout, dropout_p,
-                              dropout_seed, tile_rows, schedule=sched)
+                              dropout_seed, tile_rows, schedule=sched,
+                              tf=(tf_y, fmap[0], fmap[1]) if tf_y is not None else None)
         with self.stage("postnet"):
             chunks = output_chunks(ufo, out_chunks) if (out_chunks and chunk_cb is not None) else None
             out = self.postnet(before, (fmap[2] if fmap is not None else None, fmap[3] if fmap is not None else None, ftiles,
                                         (utt_frame_off, B)), F, chunks, chunk_cb)
+        if tf_y is not None:
+            ex.update(before=before.clone(), dlog=dlog.clone(), pitch_pred=pitch_pred.clone(), energy_pred=energy_pred.clone())
         if extras:
             ex.update(h=h, dlog=dlog, dur_pred=dur_pred, pitch=pitch, energy=energy, hn=hn, before=before,
                       frame_off=frame_off, order=order, frame_row=fmap[0], frame_step=fmap[1], position=pos,

@@ -188,8 +188,70 @@ class Tacotron2_sa(_TTSBase, torch.nn.Module):
         return int(self._dropout_seed) if self._dropout_seed is not None else (0x9E3779B97F4A7C15 * (n + 1)) & ((1 << 64) - 1)
 
     # ------------------------------------------------------------------ inference
-    def forward(self, *a, **k):
-        raise NotImplementedError("training forward()/losses are out of scope of the B200 inference path")
+    @torch.no_grad()
+    def forward_teacher_forced(self, xs, ys, durs, f0s, energies, utt_ids=None):
+        """Teacher-forced pass over a batch of utterances -- the computation of the reference's `forward()` without the
+        losses (e2e_tts_tacotron2_sa.py:520-595 -> decoder_sa.py:431-542; what the KD trainer asks of the teacher at every
+        step, tts_distill.py:159-162), in eval-mode semantics and per utterance (no padding, so no pad leakage):
+        ground-truth durations / f0 / energy condition the decoder, the decoder input of step m of a phoneme is its
+        ground-truth frame m-1 (`prev_out = y`), phonemes of duration 0 get no decoder row (decoder_sa.py:459-463).
+
+        xs: list of (N_i,) ids; ys: list of (L_i, odim) target mels with L_i = sum(durs[i]); durs / f0s / energies:
+        lists of (N_i,). -> list of dicts {after (L_i, odim), before (L_i, odim), d_outs (N_i,) log-durations of the
+        duration predictor, p_outs (N_i,), e_outs (N_i,)} (device tensors), in the order given."""
+        to_np = lambda v: v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
+        ys = [np.ascontiguousarray(to_np(y), dtype=np.float32).reshape(-1, self.odim) for y in ys]
+        pl = self._plan(xs, durs, f0s, energies, utt_ids)
+        per_utt = np.add.reduceat(pl.dur.astype(np.int64), pl.utt_off[:-1].astype(np.int64))
+        for k, i in enumerate(pl.perm):
+            if ys[int(i)].shape[0] != int(per_utt[k]):
+                raise ValueError(f"ys[{int(i)}] has {ys[int(i)].shape[0]} frames for durations summing to {int(per_utt[k])}")
+        if int(per_utt.sum()) == 0:
+            raise ValueError("every duration is zero: no frames to decode")
+        tf_y = torch.from_numpy(np.concatenate([ys[int(i)] for i in pl.perm])).to(self.device)      # processing order
+        eng = self.engine()
+        eng.skip_zero_durations = True
+        try:
+            res = eng.run(pl, self.hp.zoneout_rate, self._dropout_rate, self._seed_for_call(), tf_y=tf_y)
+        finally:
+            eng.skip_zero_durations = False
+        ex, outs = res.extras, [None] * pl.n_utts
+        for k, i in enumerate(pl.perm):
+            f0_, f1_ = int(res.utt_frame_off[k]), int(res.utt_frame_off[k + 1])
+            r0, r1 = int(pl.utt_off[k]), int(pl.utt_off[k + 1])
+            outs[int(i)] = {"after": res.out[f0_:f1_], "before": ex["before"][f0_:f1_], "d_outs": ex["dlog"][r0:r1],
+                            "p_outs": ex["pitch_pred"][r0:r1], "e_outs": ex["energy_pred"][r0:r1]}
+        return outs
+
+    @torch.no_grad()
+    def forward(self, xs, ilens, ys, olens, spembs=None, extras=None, new_ys=None, non_zero_lens_mask=None, ds_nonzeros=None,
+                output_masks=None, position=None, f0=None, energy=None, *args, **kwargs):
+        """The reference's `forward()` argument list (e2e_tts_tacotron2_sa.py:520-523; padded batch tensors from the
+        CustomConverter, tts.py:215-302) WITHOUT the losses: -> (after_outs, before_outs), both (B, Lmax, odim) zero-padded,
+        as the KD teacher's forward returns them first (e2e_tts_tacotron2_sa_kd_teacher.py:603). Training (losses,
+        gradients) stays out of scope. `extras` = durations (B, Tmax[, 1]); f0 / energy (B, Tmax[, 1]) are required
+        (use_fe_condition). The re-organised `new_ys / non_zero_lens_mask / ds_nonzeros / output_masks / position` are
+        derived on the device from the durations and ignored here. Each utterance is processed unpadded."""
+        if spembs is not None:
+            raise ValueError("speaker embeddings (spk_embed_dim) are out of scope of the B200 path")
+        if extras is None or f0 is None or energy is None:
+            raise ValueError("forward() needs the ground-truth durations (extras), f0 and energy")
+        B = int(xs.shape[0])
+        il, ol = [int(v) for v in ilens], [int(v) for v in olens]
+        ds = extras.reshape(B, -1)
+        xs_l = [xs[b, :il[b]] for b in range(B)]
+        ys_l = [ys[b, :ol[b]] for b in range(B)]
+        ds_l = [ds[b, :il[b]].long() for b in range(B)]
+        f0_l = [f0.reshape(B, -1)[b, :il[b]].float() for b in range(B)]
+        en_l = [energy.reshape(B, -1)[b, :il[b]].float() for b in range(B)]
+        outs = self.forward_teacher_forced(xs_l, ys_l, ds_l, f0_l, en_l)
+        lmax = max(ol)
+        after = torch.zeros((B, lmax, self.odim), dtype=torch.float32, device=self.device)
+        before = torch.zeros_like(after)
+        for b in range(B):
+            after[b, :ol[b]] = outs[b]["after"]
+            before[b, :ol[b]] = outs[b]["before"]
+        return after, before
 
     def _plan(self, xs, durs=None, f0s=None, energies=None, utt_ids=None):
         """Host side of a batch: validate, order longest-first, flatten (pure numpy, no CUDA calls)."""

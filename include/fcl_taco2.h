@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 21
+#define FCL_ABI_VERSION 22
 
 enum {
   FCL_OK = 0,
@@ -366,6 +366,8 @@ typedef struct {
   float dropout_p;           /* 0 => prenet dropout off                                    */
   uint64_t dropout_seed;
   int32_t tile_rows;         /* 16 or 32                                                   */
+  const float* tf_y;         /* optional (F, O): TEACHER FORCING (decoder_sa.py:431-542, `prev_out = y`): the input of
+                                step m of a row is its ground-truth frame m-1 instead of the frame it generated   */
 } FclDecoderParams;
 int fcl_decoder_f32(const FclDecoderParams* p, void* stream);
 
@@ -424,7 +426,29 @@ typedef struct {
   int32_t trace_cap;         /* capacity in records                                         */
   int32_t inflight;          /* fcl_decoder_bf16_pair: super-tiles a CTA pair keeps in flight (1 or 2; 0 = 1). With 2,
                                 act_priv and c_ws hold TWO blocks per CTA (2 * priv_bytes_per_cta, 2 * c_floats_per_cta). */
+  const void* tf_x1;         /* optional (F, prenet_units) 16-bit operand rows from fcl_prenet0_tf: TEACHER FORCING
+                                (decoder_sa.py:431-542): row f holds dropout(relu(prenet.0(y_f))), the prenet.0 output
+                                that feeds the step after frame f; the composed feat_out->prenet.0 chunk is skipped.
+                                Supported by fcl_decoder_bf16 and fcl_decoder_bf16_pair_v1.                         */
 } FclDecoderBf16Params;
+/* prenet.0 of the GROUND-TRUTH frames for the teacher-forced decoder (decoder_sa.py:146-158 applied to `prev_out = y`):
+ * x1[f] = dropout(relu(y[f] Wp0^T + b)), keyed like the inference path (utterance, phoneme, step + 1, layer 0), written
+ * as 16-bit operand rows. HBM-bound row kernel on CUDA cores (80 x 256 MACs per frame). */
+typedef struct {
+  int32_t n_frames, odim, prenet_units;
+  const float* y;            /* (F, odim) ground-truth frames, ragged-packed like the decoder's output            */
+  const int32_t* frame_row;  /* (F) phoneme row of each frame   (fcl_len_reg_frame_map)                           */
+  const int32_t* frame_step; /* (F) step of each frame within its row                                              */
+  const int32_t* row_utt;    /* (P) dropout keys                                                                   */
+  const int32_t* row_phone;
+  const float* wp0;          /* (odim, U) = prenet.0 weight^T                                                      */
+  const float* bp0;          /* (U)                                                                                */
+  float dropout_p;
+  uint64_t dropout_seed;
+  void* x1;                  /* out (F, U) 16-bit operand format                                                   */
+} FclPrenet0TfParams;
+int fcl_prenet0_tf(const FclPrenet0TfParams* p, void* stream);
+
 /* Longest-processing-time assignment of the duration-sorted tiles to the persistent CTAs (tile cost = its
  * step count + 1): every CTA ends at about the same time. One warp, ~20 us. */
 typedef struct {

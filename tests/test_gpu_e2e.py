@@ -117,8 +117,8 @@ def test_errors_are_loud(models):
         m.inference_batch([np.array([1, 2])], durs=[np.array([1])])                  # ragged mismatch
     with pytest.raises(ValueError):
         m.inference(torch.tensor([1, 2]), None, spemb=torch.zeros(4), dur=torch.tensor([1, 1]))
-    with pytest.raises(NotImplementedError):
-        m.forward()
+    with pytest.raises(ValueError):                                                   # forward() without durations / prosody
+        m.forward(torch.tensor([[1, 2]]), torch.tensor([2]), torch.zeros(1, 3, 80), torch.tensor([3]))
 
 
 @pytest.mark.gpu
