@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 22
+ABI_VERSION = 23
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -19,7 +19,7 @@ ptr = C.c_void_p
 
 class LenRegParams(C.Structure):
     _fields_ = [("n_rows", i32), ("n_utts", i32), ("dur", ptr), ("utt_off", ptr), ("frame_off", ptr),
-                ("utt_frame_off", ptr), ("order", ptr), ("totals", ptr)]
+                ("utt_frame_off", ptr), ("order", ptr), ("totals", ptr), ("ws", ptr)]
 
 
 class FrameMapParams(C.Structure):
@@ -164,7 +164,7 @@ ENTRY_POINTS = {
     "fcl_prenet0_tf": Prenet0TfParams,
 }
 PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_operand_format", "fcl_last_error", "fcl_sm_count", "fcl_struct_size",
-                 "fcl_decoder_bf16_workspace", "fcl_peer_alloc", "fcl_peer_free", "fcl_ipc_export", "fcl_ipc_open",
+                 "fcl_decoder_bf16_workspace", "fcl_len_reg_ws_ints", "fcl_peer_alloc", "fcl_peer_free", "fcl_ipc_export", "fcl_ipc_open",
                  "fcl_ipc_close", "fcl_copy_async", "fcl_wait_flags", "fcl_write_flags"]
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -205,6 +205,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(st), C.c_void_p]
+    lib.fcl_len_reg_ws_ints.restype = C.c_int
+    lib.fcl_len_reg_ws_ints.argtypes = [C.c_int32]
     lib.fcl_decoder_bf16_workspace.restype = C.c_int
     lib.fcl_decoder_bf16_workspace.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                                C.POINTER(C.c_int64)]

@@ -332,8 +332,9 @@ class Engine:
         utt_frame_off = self._buf((n_utts + 1,), torch.int32)
         order = self._buf((P,), torch.int32)
         totals = self._buf((2,), torch.int32)
+        ws = self._buf((_lib.load().fcl_len_reg_ws_ints(P),), torch.int32)       # multi-CTA scan + counting sort when P is large
         p = _lib.LenRegParams(n_rows=P, n_utts=n_utts, dur=dptr(dur), utt_off=dptr(utt_off), frame_off=dptr(frame_off),
-                              utt_frame_off=dptr(utt_frame_off), order=dptr(order), totals=dptr(totals))
+                              utt_frame_off=dptr(utt_frame_off), order=dptr(order), totals=dptr(totals), ws=dptr(ws))
         self._call("fcl_len_reg_scan", p)
         return frame_off, utt_frame_off, order, totals
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 22
+#define FCL_ABI_VERSION 23
 
 enum {
   FCL_OK = 0,
@@ -67,9 +67,13 @@ typedef struct {
   int32_t* utt_frame_off;    /* out (B+1) frame offset of each utterance                   */
   int32_t* order;            /* out (P)  rows sorted by duration, descending               */
   int32_t* totals;           /* out (2)  [0]=F total frames, [1]=max duration              */
+  int32_t* ws;               /* optional scratch of fcl_len_reg_ws_ints(n_rows) int32: enables the multi-CTA path
+                                (two launches: per-block sums + histogram, then scan + counting sort) for large batches;
+                                NULL = one CTA                                              */
 } FclLenRegParams;
-#define FCL_MAX_DURATION 1023      /* durations are clamped to this (reference data cap is 50) */
+#define FCL_MAX_DURATION 1023      /* largest supported duration (the host refuses larger ones; reference data cap is 50) */
 int fcl_len_reg_scan(const FclLenRegParams* p, void* stream);
+int fcl_len_reg_ws_ints(int32_t n_rows);
 
 typedef struct {
   int32_t n_rows, n_utts, n_frames;

@@ -37,8 +37,17 @@ def test_len_reg_bit_exact(engines):
     """duration -> frame index map must be bit-exact (north_star); incl. d=0 rows and the stress shape."""
     eng, _, _ = engines("S")
     rs = np.random.RandomState(0)
-    for case in range(4):
-        if case == 0:
+    for case in range(7):
+        if case == 4:                                     # multi-CTA scan + counting sort (P >= 8192): ragged, with zeros
+            xs, ds = synth.synth_batch(700, 4)
+            for d in ds:
+                d[rs.rand(len(d)) < 0.05] = 0
+        elif case == 5:                                   # exactly a multiple of the 4096-row block, long durations
+            xs, ds = synth.synth_batch(128, 5, fixed_len=128, stress=True)
+        elif case == 6:                                   # one row past a block boundary; a duration at the supported maximum
+            xs, ds = synth.synth_batch(1, 6, fixed_len=8193)
+            ds[0][4096] = 1023
+        elif case == 0:
             xs, ds = synth.synth_batch(5, 1)
         elif case == 1:
             xs, ds = synth.synth_batch(3, 2, fixed_len=500, stress=True)
