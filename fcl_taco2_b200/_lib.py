@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 23
+ABI_VERSION = 24
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -71,7 +71,8 @@ class LayerNormParams(C.Structure):
 
 class EmbedAddParams(C.Structure):
     _fields_ = [("rows", i32), ("chans", i32), ("taps", i32), ("h", ptr), ("pitch", ptr), ("energy", ptr),
-                ("seg_lo", ptr), ("seg_hi", ptr), ("wp", ptr), ("bp", ptr), ("we", ptr), ("be", ptr), ("hn", ptr)]
+                ("seg_lo", ptr), ("seg_hi", ptr), ("wp", ptr), ("bp", ptr), ("we", ptr), ("be", ptr), ("hn", ptr),
+                ("order", ptr), ("img", ptr)]
 
 
 class BiLstmParams(C.Structure):

@@ -53,6 +53,13 @@ __device__ __forceinline__ void prefetch_gx16(const FclBiLstmBf16Params& p, long
   asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
 }
 
+// one mbarrier arrival per epilogue WARP (the lanes' tcgen05.ld / fenced shared-memory writes are ordered before lane 0's
+// arrive by the warp barrier): 16 arrivals per hand-over instead of 512 on the per-step critical path
+__device__ __forceinline__ void warp_arrive1(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
 struct BlShared {
   uint64_t full[4], empty[4];
   uint64_t tmem_full[2], tmem_empty[2];
@@ -81,8 +88,8 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&sh.tmem_full[b], 1); mbar_init(&sh.tmem_empty[b], kBlEpiThreads); }
-    mbar_init(&sh.h_ready, kBlEpiThreads);
+    for (int b = 0; b < 2; ++b) { mbar_init(&sh.tmem_full[b], 1); mbar_init(&sh.tmem_empty[b], kBlEpiThreads / 32); }
+    mbar_init(&sh.h_ready, kBlEpiThreads / 32);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&sh.tmem_base, 512);
@@ -158,7 +165,7 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
     // zero the first h image (this thread's quarter of the k-chunks)
     for (int kc = cs; kc < H / 8; kc += 4) *reinterpret_cast<uint4*>(himg + ((size_t)kc * 128 + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
-    mbar_arrive(&sh.h_ready);
+    warp_arrive1(&sh.h_ready, lane);
 
     if (R == 32) {
       // ---- replicated mode: the 32 utterances of the tile occupy all four 32-row quarters of the M = 128 operand
@@ -211,7 +218,7 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
               if (active) creg[c][j] = cn;
             }
             tc_fence_before();
-            mbar_arrive(&sh.tmem_empty[buf]);
+            warp_arrive1(&sh.tmem_empty[buf], lane);
             ++chunk_ctr;
             const uint2 hw = make_uint2(pack_op(hf[0], hf[1]), pack_op(hf[2], hf[3]));
 #pragma unroll
@@ -222,7 +229,7 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(&sh.h_ready);
+        warp_arrive1(&sh.h_ready, lane);
       }
     } else
     for (int t = 0; t < steps; ++t) {
@@ -279,7 +286,7 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
           hout[2 * g + 1] = pack_op(hf[g * 4 + 2], hf[g * 4 + 3]);
         }
         tc_fence_before();
-        mbar_arrive(&sh.tmem_empty[buf]);
+        warp_arrive1(&sh.tmem_empty[buf], lane);
         ++chunk_ctr;
         *reinterpret_cast<uint4*>(hnew + ((size_t)(u0 >> 3) * 128 + r) * 16) = make_uint4(hout[0], hout[1], hout[2], hout[3]);
         *reinterpret_cast<uint4*>(hnew + ((size_t)((u0 >> 3) + 1) * 128 + r) * 16) = make_uint4(hout[4], hout[5], hout[6], hout[7]);
@@ -290,7 +297,7 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive(&sh.h_ready);
+      warp_arrive1(&sh.h_ready, lane);
     }
   }
   tc_fence_before();

@@ -120,6 +120,97 @@ embed_add_kernel(FclEmbedAddParams p) {
   }
 }
 
+// Same arithmetic, but the result goes straight into the decoder's operand image in duration-sorted tile order:
+// hn never exists in fp32. A WARP owns 8 consecutive sorted rows (one 128-byte run of every 8-channel slab of the image):
+// lane = slab, so h[row] is one coalesced 1 KB read, the row's 18 pitch / energy taps are fetched once by lanes 0-17 and
+// broadcast with shuffles, and each lane finally writes its own 8 x 16 contiguous bytes. No shared-memory staging, no
+// block barrier in the loop.
+__global__ void __launch_bounds__(256)
+embed_add_pack_kernel(FclEmbedAddParams p) {
+  extern __shared__ __align__(16) float sw[];
+  float* swp = sw;
+  float* swe = sw + (size_t)p.taps * p.chans;
+  for (int i = threadIdx.x; i < p.taps * p.chans; i += blockDim.x) {
+    const int j = i / p.chans, c = i - j * p.chans;
+    swp[i] = p.wp[(size_t)c * p.taps + j];
+    swe[i] = p.we[(size_t)c * p.taps + j];
+  }
+  __syncthreads();
+  const int c8 = p.chans >> 3, taps = p.taps, half = taps >> 1;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_groups = ((p.rows + 127) >> 7) * 16;                 // groups of 8 sorted rows (tiles are padded to 128)
+  for (int grp = gw; grp < n_groups; grp += warps) {
+    // lane l < 8: metadata of row l of the group
+    int my_r = -1, my_lo = 0, my_hi = 0;
+    if (lane < 8 && grp * 8 + lane < p.rows) { my_r = p.order[grp * 8 + lane]; my_lo = p.seg_lo[my_r]; my_hi = p.seg_hi[my_r]; }
+    const int tile = grp >> 4, ri0 = (grp & 15) * 8;
+    for (int kc0 = 0; kc0 < c8; kc0 += 32) {
+      const int kc = kc0 + lane, c = kc * 8;
+      const bool mine = kc < c8;
+      uint4* dst = reinterpret_cast<uint4*>(p.img) + ((size_t)tile * c8 + (mine ? kc : 0)) * 128 + ri0;
+      // four rows at a time share every weight read: the 18 KB of embedding weights would otherwise be re-read from
+      // shared memory for each row (measured: the kernel was shared-memory-bandwidth bound, 82 % L1TEX throughput)
+#pragma unroll 1
+      for (int q0 = 0; q0 < 8; q0 += 4) {
+        int rq[4];
+        float tv[4], ap[4][8], ae[4][8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = __shfl_sync(0xffffffffu, my_r, q0 + q), lo = __shfl_sync(0xffffffffu, my_lo, q0 + q),
+                    hi = __shfl_sync(0xffffffffu, my_hi, q0 + q);
+          rq[q] = r;
+          // lanes 0 .. taps-1: pitch taps, lanes 16 .. 16+taps-1: energy taps (zero outside the utterance)
+          const int j = lane & 15, src = r + j - half;
+          tv[q] = (r >= 0 && j < taps && src >= lo && src < hi) ? __ldg((lane < 16 ? p.pitch : p.energy) + src) : 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { ap[q][k] = 0.f; ae[q][k] = 0.f; }
+        }
+        for (int j = 0; j < taps; ++j) {
+          float4 wp0 = make_float4(0.f, 0.f, 0.f, 0.f), wp1 = wp0, we0 = wp0, we1 = wp0;
+          if (mine) {
+            wp0 = *reinterpret_cast<const float4*>(swp + (size_t)j * p.chans + c); wp1 = *reinterpret_cast<const float4*>(swp + (size_t)j * p.chans + c + 4);
+            we0 = *reinterpret_cast<const float4*>(swe + (size_t)j * p.chans + c); we1 = *reinterpret_cast<const float4*>(swe + (size_t)j * p.chans + c + 4);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float pv = __shfl_sync(0xffffffffu, tv[q], j), ev = __shfl_sync(0xffffffffu, tv[q], 16 + j);
+            ap[q][0] = fmaf(wp0.x, pv, ap[q][0]); ap[q][1] = fmaf(wp0.y, pv, ap[q][1]); ap[q][2] = fmaf(wp0.z, pv, ap[q][2]); ap[q][3] = fmaf(wp0.w, pv, ap[q][3]);
+            ap[q][4] = fmaf(wp1.x, pv, ap[q][4]); ap[q][5] = fmaf(wp1.y, pv, ap[q][5]); ap[q][6] = fmaf(wp1.z, pv, ap[q][6]); ap[q][7] = fmaf(wp1.w, pv, ap[q][7]);
+            ae[q][0] = fmaf(we0.x, ev, ae[q][0]); ae[q][1] = fmaf(we0.y, ev, ae[q][1]); ae[q][2] = fmaf(we0.z, ev, ae[q][2]); ae[q][3] = fmaf(we0.w, ev, ae[q][3]);
+            ae[q][4] = fmaf(we1.x, ev, ae[q][4]); ae[q][5] = fmaf(we1.y, ev, ae[q][5]); ae[q][6] = fmaf(we1.z, ev, ae[q][6]); ae[q][7] = fmaf(we1.w, ev, ae[q][7]);
+          }
+        }
+        if (mine) {
+          const float4 bp0 = __ldg(reinterpret_cast<const float4*>(p.bp + c)), bp1 = __ldg(reinterpret_cast<const float4*>(p.bp + c) + 1);
+          const float4 be0 = __ldg(reinterpret_cast<const float4*>(p.be + c)), be1 = __ldg(reinterpret_cast<const float4*>(p.be + c) + 1);
+          const float bpv[8] = {bp0.x, bp0.y, bp0.z, bp0.w, bp1.x, bp1.y, bp1.z, bp1.w};
+          const float bev[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            if (rq[q] >= 0) {
+              const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)rq[q] * p.chans + c));
+              const float4 h1 = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)rq[q] * p.chans + c) + 1);
+              float acc[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+              for (int k = 0; k < 8; ++k)  // same association as the reference: (h + p_emb) + e_emb, embeds carry their bias
+                acc[k] = (acc[k] + (ap[q][k] + bpv[k])) + (ae[q][k] + bev[k]);
+              if (p.hn) {
+                float4* o = reinterpret_cast<float4*>(p.hn + (size_t)rq[q] * p.chans + c);
+                o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+              }
+              w = make_uint4(umma::pack_op(acc[0], acc[1]), umma::pack_op(acc[2], acc[3]), umma::pack_op(acc[4], acc[5]), umma::pack_op(acc[6], acc[7]));
+            }
+            dst[q0 + q] = w;
+          }
+        }
+      }
+    }
+  }
+}
+
 // gather rows by `order`, round to bf16, write the UMMA operand image [tile][cols/8][128][8]
 __global__ void __launch_bounds__(256)
 pack_rows_bf16_kernel(FclPackRowsParams p) {
@@ -221,9 +312,10 @@ extern "C" int fcl_layernorm_f32(const FclLayerNormParams* p, void* stream) {
 
 extern "C" int fcl_embed_add_f32(const FclEmbedAddParams* p, void* stream) {
   using namespace fcl;
-  FCL_REQUIRE(p && p->h && p->pitch && p->energy && p->seg_lo && p->seg_hi && p->wp && p->bp && p->we && p->be && p->hn,
-              "null pointer");
+  FCL_REQUIRE(p && p->h && p->pitch && p->energy && p->seg_lo && p->seg_hi && p->wp && p->bp && p->we && p->be &&
+                  (p->hn || p->img), "null pointer");
   FCL_REQUIRE(p->rows > 0 && p->chans % 4 == 0 && (p->taps & 1), "bad sizes");
+  FCL_REQUIRE(!p->img || (p->order && p->chans % 8 == 0), "the packed form needs `order` and chans % 8 == 0");
   int sms = fcl_sm_count();
   if (sms < 0) return sms;
   size_t total = (size_t)p->rows * (p->chans / 4);
@@ -231,6 +323,12 @@ extern "C" int fcl_embed_add_f32(const FclEmbedAddParams* p, void* stream) {
   const size_t smem = (size_t)2 * p->taps * p->chans * sizeof(float);
   FCL_REQUIRE(smem <= 48 * 1024, "embed weights do not fit the static shared-memory window");
   blocks = min(blocks, sms * 4);
+  if (p->img) {
+    FCL_REQUIRE(p->taps <= 15, "the packed form supports at most 15 taps");
+    const int groups = ((p->rows + 127) / 128) * 16;                 // one warp per group of 8 sorted rows
+    embed_add_pack_kernel<<<min((groups + 7) / 8, sms * 8), 256, smem, as_stream(stream)>>>(*p);
+    return check_launch("fcl_embed_add_f32");
+  }
   embed_add_kernel<<<blocks, 256, smem, as_stream(stream)>>>(*p);
   return check_launch("fcl_embed_add_f32");
 }

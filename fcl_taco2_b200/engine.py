@@ -316,14 +316,19 @@ class Engine:
                        head_b=self.head_b[name], head_out=head, dur_out=dur)
         return head, dur
 
-    def embed_add(self, h, pitch, energy, seg):
+    def embed_add(self, h, pitch, energy, seg, order=None, want_rows=True):
+        """hn = h + pitch_embed + energy_embed. With `order` (tensor-core decoder) the result is also / only written as
+        the decoder's operand image in duration-sorted tile order. -> (hn rows or None, image or None)"""
         hp, w = self.hp, self.w
-        hn = self._buf(tuple(h.shape), torch.float32)
-        p = _lib.EmbedAddParams(rows=h.shape[0], chans=hp.eunits, taps=hp.embed_kernel, h=dptr(h), pitch=dptr(pitch),
+        P, E = h.shape[0], hp.eunits
+        hn = self._buf(tuple(h.shape), torch.float32) if (want_rows or order is None) else None
+        img = self._buf((((P + 127) // 128) * 128 * E,), self.op_dtype) if order is not None else None
+        p = _lib.EmbedAddParams(rows=P, chans=E, taps=hp.embed_kernel, h=dptr(h), pitch=dptr(pitch),
                                 energy=dptr(energy), seg_lo=dptr(seg[0]), seg_hi=dptr(seg[1]), wp=dptr(w["pemb_w"]),
-                                bp=dptr(w["pemb_b"]), we=dptr(w["eemb_w"]), be=dptr(w["eemb_b"]), hn=dptr(hn))
+                                bp=dptr(w["pemb_b"]), we=dptr(w["eemb_w"]), be=dptr(w["eemb_b"]), hn=dptr(hn),
+                                order=dptr(order), img=dptr(img))
         self._call("fcl_embed_add_f32", p)
-        return hn
+        return hn, img
 
     def len_reg_scan(self, dur, utt_off, n_utts):
         P = dur.shape[0]
@@ -349,10 +354,11 @@ class Engine:
         return buf, pos
 
     def decoder(self, hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p, dropout_seed,
-                tile_rows=None, schedule=None, tf=None):
-        """`tf` = (ys (F, O) fp32 ground-truth frames in output order, frame_row, frame_step): teacher forcing."""
+                tile_rows=None, schedule=None, tf=None, hn_img=None):
+        """`tf` = (ys (F, O) fp32 ground-truth frames in output order, frame_row, frame_step): teacher forcing.
+        `hn_img`: hn already packed as the tensor-core decoder's operand image (Engine.embed_add with `order`)."""
         hp, w = self.hp, self.w
-        P, E, H, O = hn.shape[0], hp.eunits, hp.dunits, hp.odim
+        P, E, H, O = order.shape[0], hp.eunits, hp.dunits, hp.odim
         if self.precision != "fp32" and self.bf16_decoder:
             tf_x1 = None
             if tf is not None:
@@ -363,7 +369,7 @@ class Engine:
                     frame_step=dptr(tf[2]), row_utt=dptr(row_utt), row_phone=dptr(row_phone), wp0=dptr(w["dec_wp0"]),
                     bp0=dptr(w["dec_bp0"]), dropout_p=dropout_p, dropout_seed=dropout_seed, x1=dptr(tf_x1)))
             return self.decoder_bf16(hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p,
-                                     dropout_seed, schedule, tf_x1=tf_x1)
+                                     dropout_seed, schedule, tf_x1=tf_x1, hn_img=hn_img)
         with self.stage("decoder_hoist"):
             g0h = self.conv_gemm(hn, w["dec_g0h_w"], w["dec_g0h_b"], P, E, 4 * H, 1, ACT_NONE)
             y0h = self.conv_gemm(hn, w["dec_y0h_w"], None, P, E, O, 1, ACT_NONE)
@@ -414,16 +420,17 @@ class Engine:
         return group, n_groups, n_slots, sched
 
     def decoder_bf16(self, hn, dur, frame_off, order, row_utt, row_phone, n_frames, zoneout, dropout_p, dropout_seed,
-                     schedule=None, tf_x1=None):
+                     schedule=None, tf_x1=None, hn_img=None):
         """Tensor-core decoder: h packed as a bf16 operand image in duration-sorted tile order, then the
         persistent tcgen05 loop."""
         hp, w = self.hp, self.w
-        P, E, H, O = hn.shape[0], hp.eunits, hp.dunits, hp.odim
+        P, E, H, O = order.shape[0], hp.eunits, hp.dunits, hp.odim
         n_tiles = (P + 127) // 128
-        with self.stage("decoder_hoist"):
-            hn_img = self._buf((n_tiles * 128 * E,), self.op_dtype)
-            self._call("fcl_pack_rows_bf16", _lib.PackRowsParams(n_rows=P, cols=E, src=dptr(hn), ld=E, order=dptr(order),
-                                                                 dst=dptr(hn_img)))
+        if hn_img is None:
+            with self.stage("decoder_hoist"):
+                hn_img = self._buf((n_tiles * 128 * E,), self.op_dtype)
+                self._call("fcl_pack_rows_bf16", _lib.PackRowsParams(n_rows=P, cols=E, src=dptr(hn), ld=E, order=dptr(order),
+                                                                     dst=dptr(hn_img)))
         group, n_groups, n_slots, sched = schedule if schedule is not None else self.decoder_schedule(order, dur, P)
         before = self._buf((max(n_frames, 1), O), torch.float32)
         trace = getattr(self, "dec_trace", None)
@@ -695,7 +702,6 @@ class Engine:
                 pitch, energy = pitch_pred, energy_pred
             else:
                 pitch, energy = d["pitch"], d["energy"]
-            hn = self.embed_add(h, pitch, energy, seg)
         if need_pred_dur:
             frame_off, utt_frame_off, order, totals, sched, _, _, _ = length_regulation(dur, None)
             host = torch.cat([totals, utt_frame_off]).cpu().numpy()      # the one data-dependent D2H sync
@@ -717,11 +723,15 @@ class Engine:
             frame_off, utt_frame_off, order, totals, sched, fmap, pos, ftiles = lr
             if use_side:
                 main.wait_stream(side)
+        tc_dec = self.precision != "fp32" and self.bf16_decoder
+        with self.stage("embed_add"):       # pitch / energy embeddings + add; on the tensor-core path straight into the
+            hn, hn_img = self.embed_add(h, pitch, energy, seg, order=order if tc_dec else None,   # decoder's operand image
+                                        want_rows=extras or not tc_dec)
         if tf_y is not None and tuple(tf_y.shape) != (F, hp.odim):
             raise ValueError(f"teacher forcing: {tuple(tf_y.shape)} target frames for {F} frames of duration")
         before = self.decoder(hn, dur, frame_off, order, d["row_utt"], d["row_phone"], F, zoneout, dropout_p,
                               dropout_seed, tile_rows, schedule=sched,
-                              tf=(tf_y, fmap[0], fmap[1]) if tf_y is not None else None)
+                              tf=(tf_y, fmap[0], fmap[1]) if tf_y is not None else None, hn_img=hn_img)
         with self.stage("postnet"):
             chunks = output_chunks(ufo, out_chunks) if (out_chunks and chunk_cb is not None) else None
             out = self.postnet(before, (fmap[2] if fmap is not None else None, fmap[3] if fmap is not None else None, ftiles,

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 23
+#define FCL_ABI_VERSION 24
 
 enum {
   FCL_OK = 0,
@@ -295,7 +295,11 @@ typedef struct {
   const float* bp;
   const float* we;
   const float* be;
-  float* hn;                 /* out (rows, chans) */
+  float* hn;                 /* out (rows, chans); may be NULL when `img` is given */
+  const int32_t* order;      /* optional (rows): with `img`, the decoder's duration-sorted row order (fcl_len_reg_scan) */
+  void* img;                 /* optional out: hn as the decoder's 16-bit operand image [ceil(rows/128)][chans/8][128][8],
+                                image row (tile*128 + i) = hn row order[tile*128 + i] (what fcl_pack_rows_bf16 would
+                                produce from hn), written directly: no fp32 round trip through HBM */
 } FclEmbedAddParams;
 int fcl_embed_add_f32(const FclEmbedAddParams* p, void* stream);
 

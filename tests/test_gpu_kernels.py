@@ -91,8 +91,18 @@ def test_encoder_and_predictors(engines, kind):
     dlog, dur = eng.predictor("dur", h, seg, want_dur=True)
     pit, _ = eng.predictor("pitch", h, seg)
     ene, _ = eng.predictor("energy", h, seg)
-    hn = eng.embed_add(h, pit, ene, seg)
+    hn, _ = eng.embed_add(h, pit, ene, seg)
+    # packed form: straight into the tensor-core decoder's operand image == fcl_pack_rows_bf16(hn), bit for bit
+    from fcl_taco2_b200 import _lib, pack
+    from fcl_taco2_b200._lib import dptr
+    order = torch.randperm(pl.n_rows, generator=torch.Generator().manual_seed(0)).to(torch.int32).cuda()
+    eng.op_dtype = pack.op_dtype()
+    hn2, img = eng.embed_add(h, pit, ene, seg, order=order, want_rows=True)
+    ref_img = torch.empty_like(img)
+    _lib.call("fcl_pack_rows_bf16", _lib.PackRowsParams(n_rows=pl.n_rows, cols=hp.eunits, src=dptr(hn), ld=hp.eunits,
+                                                        order=dptr(order), dst=dptr(ref_img)), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
+    assert torch.equal(hn2, hn) and torch.equal(img.view(torch.int16), ref_img.view(torch.int16))
     for k, i in enumerate(pl.perm):
         lo, hi = pl.utt_off[k], pl.utt_off[k + 1]
         x = torch.from_numpy(xs[i])
