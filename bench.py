@@ -102,7 +102,11 @@ class ClockSampler:
                     reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
                 except Exception:
                     reasons = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                self.samples.append((mhz, reasons))
+                try:
+                    mem = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_MEM))
+                except Exception:
+                    mem = 0.0
+                self.samples.append((mhz, reasons, mem))
             except Exception:
                 pass
             time.sleep(0.01)
@@ -124,10 +128,11 @@ class ClockSampler:
                      "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
                      "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
                      "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
-            reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r in sel))
-            mhz = [m for m, _ in sel if m > 0]
+            reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r, _m in sel))
+            mhz = [m for m, _, _m in sel if m > 0]
+            mem = [mm for _, _, mm in sel if mm > 0]
             return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                    "samples": len(sel), "source": "nvml"}
+                    "mem_mhz": float(np.median(mem)) if mem else None, "samples": len(sel), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -148,6 +153,23 @@ class ClockSampler:
         busy = [s for s in sm if s > 0]
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
+
+
+def hbm_copy_probe(dev, nbytes=1 << 30):
+    """Device-to-device copy bandwidth of THIS box right before the run (read + write bytes, best of 5, CUDA events;
+    outside every timed region): the HBM-bound stages (postnet, L2 flush, the decoder's scratch traffic) scale with it,
+    so a slow step can be told from a slow box."""
+    a = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    a.fill_(1)
+    best = 0.0
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); b.copy_(a); e1.record()
+        torch.cuda.synchronize(dev)
+        best = max(best, 2.0 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    del a, b
+    return {"copy_gbs": best, "bytes": nbytes, "how": "torch b.copy_(a), read+write bytes, best of 6, before the timed region"}
 
 
 def workload(args, rank):
@@ -433,6 +455,7 @@ def main():
     arm = Arm(m, xs, ds)
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
     pk = peaks()
+    hbm_probe = hbm_copy_probe(dev) if rank == 0 else None
 
     # groups of utterances whose mels are handed to the gather while the next group's postnet runs
     K_CHUNKS = 1 if world <= 2 else 4
@@ -537,6 +560,7 @@ def main():
             "config": config_dict(args, world),
             "frames_per_step": all_frames, "phoneme_rows_per_step": all_rows,
             "clocks": clocks,
+            "hbm_probe": hbm_probe,
             "e2e": {"value": all_frames * args.steps / (e2e_ms * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": int(arm.h2d_bytes), "d2h_bytes_per_step": int(n_frames * m.odim * 4),
                     "ms_per_step": e2e_ms / args.steps},

@@ -10,8 +10,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 24
+# FCL_TACO2_LIB selects another build of the same library (tools: the -DFCL_DEC_PROF profiling build)
+LIB_PATH = os.environ.get("FCL_TACO2_LIB") or os.path.join(_HERE, "lib", "libfcl_taco2.so")
+ABI_VERSION = 27
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p

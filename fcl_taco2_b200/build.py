@@ -25,15 +25,24 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+PROF_LIB = os.path.join(HERE, "lib", "libfcl_taco2_prof.so")
+
+
+def build(force: bool = False, verbose: bool = False, prof: bool = False) -> str:
+    """`prof=True`: the profiling build (-DFCL_DEC_PROF: counter-mode probes and what-if switches in the pair decoders,
+    tools/decoder_prof.py) as lib/libfcl_taco2_prof.so; the product library carries none of it."""
+    if prof:
+        out, extra = PROF_LIB, ["-DFCL_DEC_PROF"]
+    else:
+        if not force and not needs_build():
+            return LIB
+        out, extra = LIB, []
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", LIB]
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return out

@@ -445,12 +445,16 @@ class Engine:
                                    zoneout=zoneout,
                                    dropout_p=dropout_p, dropout_seed=dropout_seed, tile_slot=dptr(sched[0]),
                                    tile_rank=dptr(sched[1]), trace=dptr(trace),
-                                   trace_cap=(trace.numel() - 2) // 2 if trace is not None else 0,
+                                   trace_cap=(-1 if getattr(self, "dec_prof", False) else (trace.numel() - 2) // 2) if trace is not None else 0,
                                    inflight=self.pair_inflight, tf_x1=dptr(tf_x1))
         with self.stage("decoder_loop"):
-            self._call(("fcl_decoder_bf16_pair_v1" if (self.pair_kernel == "v1" or tf_x1 is not None) else "fcl_decoder_bf16_pair")
-                       if group < 0 else "fcl_decoder_bf16", p)
+            self._call(self._pair_entry(tf_x1 is not None) if group < 0 else "fcl_decoder_bf16", p)
         return before
+
+    def _pair_entry(self, teacher_forcing):
+        if self.pair_kernel == "v2" and not teacher_forcing:
+            return "fcl_decoder_bf16_pair"
+        return "fcl_decoder_bf16_pair_v1"
 
     def conv_stack(self, keys, acts, x, ld_in, rows, seg_off, n_segs, max_len_sum_tiles, taps=5, gather=None,
                    residual=None, wkeys=None, final=False, out=None):

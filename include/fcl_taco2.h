@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 24
+#define FCL_ABI_VERSION 27
 
 enum {
   FCL_OK = 0,
@@ -479,7 +479,9 @@ int fcl_decoder_bf16(const FclDecoderBf16Params* p, void* stream);
 /* act_priv / c_ws are indexed with TWO blocks per CTA in this kernel whatever `inflight` is. */
 int fcl_decoder_bf16_pair(const FclDecoderBf16Params* p, void* stream);
 /* Round-1 form of the same kernel (one super-tile per pair at a time, per-role tile loops instead of the slot scheduler):
- * same parameters and results; `inflight` is ignored and act_priv / c_ws are indexed with ONE block per CTA. */
+ * same parameters and results; `inflight` is ignored and act_priv / c_ws are indexed with ONE block per CTA.
+ * The engine's default for large batches. When they fit (S-sized models: 14 KB) the epilogue constants (gate biases,
+ * position column, prenet biases) are staged in shared memory behind the ring. */
 int fcl_decoder_bf16_pair_v1(const FclDecoderBf16Params* p, void* stream);
 
 /* ---------------------------------------------------------------- multi-GPU: peer-memory gather plumbing
