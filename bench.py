@@ -310,10 +310,15 @@ def time_arm(arm, steps, warmup, dropout, flush, dist=None, dev=None, gather=Non
         barrier()
     finally:
         gc.enable()
-    stage_ms = {}
+    stage_ms, per_step = {}, {}
     for se in stage_evs:
         for name, a, b in se:
-            stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b) / steps
+            dt = a.elapsed_time(b)
+            stage_ms[name] = stage_ms.get(name, 0.0) + dt / steps
+            per_step.setdefault(name, []).append(dt)
+    if os.environ.get("FCL_BENCH_DEBUG"):          # per-step stage times: tells a slow kernel from a one-off stall
+        for name, v in per_step.items():
+            print(f"[bench debug] {name}: " + " ".join(f"{x:.3f}" for x in v), flush=True)   # fd 1 is stderr here
     n_frames = arm.n_frames if arm.n_frames is not None else int(res.out.shape[0])
     return dict(total_ms=float(e0.elapsed_time(e1)), stage_ms=stage_ms, launches=(eng.launches - launches0) / steps,
                 frames=n_frames, rows=arm.n_rows, res=res, bufs=bufs)

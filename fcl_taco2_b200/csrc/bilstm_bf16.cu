@@ -88,7 +88,9 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&sh.tmem_full[b], 1); mbar_init(&sh.tmem_empty[b], kBlEpiThreads / 32); }
+    // split mode (below): a chunk's accumulator is drained by one HALF of the epilogue warps
+    const bool split = p.tile_utts == 32 && (nch & 1) == 0;
+    for (int b = 0; b < 2; ++b) { mbar_init(&sh.tmem_full[b], 1); mbar_init(&sh.tmem_empty[b], (kBlEpiThreads / 32) / (split ? 2 : 1)); }
     mbar_init(&sh.h_ready, kBlEpiThreads / 32);
     fence_barrier_init();
   }
@@ -103,7 +105,10 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
     if (elect_one()) {
       uint32_t stage = 0, sphase = 0;
       const uint8_t* wdir = reinterpret_cast<const uint8_t*>(p.whh_packed) + (size_t)dir * nch * kH * kBlBBytes;
-      for (int t = 0; t < steps; ++t) {
+      // W_hh RESIDENT (H = 128: the ring holds all nch * kH stages): copied once, never refilled -- the issuer then has no
+      // full / empty traffic on its per-step critical path
+      const int n_loads = (nch * kH <= stages) ? min(steps, 1) : steps;
+      for (int t = 0; t < n_loads; ++t) {
         const uint8_t* wptr = wdir;
         for (int i = 0; i < nch * kH; ++i) {
           mbar_wait(&sh.empty[stage], sphase ^ 1u);
@@ -120,27 +125,38 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
     if (elect_one()) {
       uint32_t stage = 0, sphase = 0, chunk_ctr = 0;
       const uint32_t idesc = idesc_op_f32(128u, 256u);
+      const bool resident = nch * kH <= stages;
+      // descriptors as in the decoder kernels: high word constant (SBO 128 B, version 1), low word = (address >> 4) |
+      // (LBO >> 4) << 16 built with one add per MMA -- this thread's instruction chain is on the step's critical path
+      constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+      constexpr uint32_t kALo = (2048u >> 4) << 16, kBLo = (4096u >> 4) << 16;
+      const uint32_t ring_lo = smem_u32(smem) >> 4;
       for (int t = 0; t < steps; ++t) {
         mbar_wait(&sh.h_ready, (uint32_t)t & 1u);          // h(t-1) image complete (t = 0: zeros)
         tc_fence_after();
-        const uint32_t a_base = smem_u32(himg + (size_t)(t & 1) * himg_bytes);
+        uint32_t a_lo = (smem_u32(himg + (size_t)(t & 1) * himg_bytes) >> 4) + kALo;
         for (int c = 0; c < nch; ++c) {
           const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
           mbar_wait(&sh.tmem_empty[buf], (use & 1u) ^ 1u);
           tc_fence_after();
+          const uint32_t d_tmem = tmem + buf * 256u;
           for (int ks = 0; ks < kH; ++ks) {
-            mbar_wait(&sh.full[stage], sphase);
-            tc_fence_after();
-            const uint32_t b_addr = smem_u32(smem + (size_t)stage * kBlBBytes);
+            if (!resident || t == 0) {
+              mbar_wait(&sh.full[stage], sphase);
+              tc_fence_after();
+            }
+            const uint32_t b_lo = ring_lo + (uint32_t)stage * (kBlBBytes >> 4) + kBLo;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = smem_desc(a_base + (uint32_t)(ks * 4 + k) * 4096u, 2048u, 128u);
-              const uint64_t bd = smem_desc(b_addr + (uint32_t)k * 8192u, 4096u, 128u);
-              mma_bf16_ss(tmem + buf * 256u, ad, bd, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+              const uint64_t ad = ((uint64_t)kDescHi << 32) | (a_lo + (uint32_t)k * (4096u >> 4));
+              const uint64_t bd = ((uint64_t)kDescHi << 32) | (b_lo + (uint32_t)k * (8192u >> 4));
+              mma_bf16_ss(d_tmem, ad, bd, idesc, (ks > 0 || k > 0) ? 1u : 0u);
             }
-            mma_commit(&sh.empty[stage]);
-            if (++stage == (uint32_t)stages) { stage = 0; sphase ^= 1u; }
+            a_lo += 4u * (4096u >> 4);
+            if (!resident) mma_commit(&sh.empty[stage]);
+            if (++stage == (uint32_t)(resident ? nch * kH : stages)) { stage = 0; sphase ^= 1u; }
           }
+          a_lo -= (uint32_t)kH * 4u * (4096u >> 4);
           mma_commit(&sh.tmem_full[buf]);
           ++chunk_ctr;
         }
@@ -167,7 +183,85 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
     fence_proxy_async_smem();
     warp_arrive1(&sh.h_ready, lane);
 
-    if (R == 32) {
+    if (R == 32 && (nch & 1) == 0) {
+      // ---- replicated + split mode (even chunk counts: H = 128, 256). As below the 32 utterances of the tile occupy all
+      // four 32-row quarters of the M = 128 operand, but the chunks of a step are dealt to the two HALVES of the epilogue
+      // warps (chunk c -> half c & 1 == its accumulator buffer): both halves update cells at the same time, each thread
+      // 8 hidden units of its chunk, instead of all warps doing 4 units of every chunk one chunk after the other. The
+      // step is a latency chain (MMA -> wake -> update -> fence -> arrive -> wake) and the chunk epilogues were its longer
+      // part (S batch 1024: 0.42 -> see profiles/r02_bilstm.md).
+      const int uu = u_first + lane;
+      int off2 = 0, len2 = 0;
+      long poff2 = 0;
+      if (uu < p.n_utts) {
+        off2 = p.utt_off[uu]; len2 = p.utt_off[uu + 1] - off2;
+        if (p.prow_off) poff2 = p.prow_off[uu];
+      }
+      const int half = cs >> 1;                              // which chunks (c & 1 == half) and which accumulator buffer
+      const int usub = ((cs & 1) * 4 + q) * 8;               // first of this thread's 8 units within a 64-unit chunk
+      float creg[2][8];                                      // chunks half, half + 2
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) creg[c][j] = 0.f;
+      uint32_t my_use = 0;                                   // uses of accumulator buffer `half` so far
+      for (int t = 0; t < steps; ++t) {
+        const bool active = t < len2;
+        const int tt = dir == 0 ? t : len2 - 1 - t;
+        const int grow = off2 + tt;
+        const long gprow = poff2 + tt;
+        uint8_t* hnew = himg + (size_t)((t + 1) & 1) * himg_bytes;
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c = half + 2 * ci;
+          if (c < nch) {
+            const int ub = c * 64 + usub;
+            const int col = dir * 4 * H + 4 * ub;            // gate-interleaved column of unit ub, gate i
+            float gq[2][16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) gq[0][j] = gq[1][j] = 0.f;
+            if (active) {                                    // requested before waiting for the accumulator
+              load_gx16(p, grow, gprow, col, gq[0]);
+              load_gx16(p, grow, gprow, col + 16, gq[1]);
+              if (t + 1 < len2) {                            // pull the next step's gx into L2
+                prefetch_gx16(p, grow + (dir == 0 ? 1 : -1), gprow + (dir == 0 ? 1 : -1), col);
+                if (p.gx_blk) prefetch_gx16(p, grow + (dir == 0 ? 1 : -1), gprow + (dir == 0 ? 1 : -1), col + 16);
+              }
+            }
+            mbar_wait(&sh.tmem_full[half], my_use & 1u);
+            tc_fence_after();
+            float hf[8];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              float v[16];
+              tmem_ld16(lane_addr + (uint32_t)half * 256u + (uint32_t)(usub * 4 + g * 16), v);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float ig = sigmoid_fast(v[4 * j] + gq[g][4 * j]), fg = sigmoid_fast(v[4 * j + 1] + gq[g][4 * j + 1]);
+                const float cg = tanh_fast(v[4 * j + 2] + gq[g][4 * j + 2]), og = sigmoid_fast(v[4 * j + 3] + gq[g][4 * j + 3]);
+                const float cn = fmaf(fg, creg[ci][g * 4 + j], ig * cg);
+                hf[g * 4 + j] = active ? og * tanh_fast(cn) : 0.f;
+                if (active) creg[ci][g * 4 + j] = cn;
+              }
+            }
+            tc_fence_before();
+            warp_arrive1(&sh.tmem_empty[half], lane);
+            ++my_use;
+            const uint4 hw = make_uint4(pack_op(hf[0], hf[1]), pack_op(hf[2], hf[3]), pack_op(hf[4], hf[5]), pack_op(hf[6], hf[7]));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)                      // all four replicas of this utterance's row
+              *reinterpret_cast<uint4*>(hnew + ((size_t)(ub >> 3) * 128 + k * 32 + lane) * 16) = hw;
+            if (active) {
+              float4* o = reinterpret_cast<float4*>(p.out + (size_t)grow * 2 * H + (size_t)dir * H + ub);
+              o[0] = make_float4(hf[0], hf[1], hf[2], hf[3]);
+              o[1] = make_float4(hf[4], hf[5], hf[6], hf[7]);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        warp_arrive1(&sh.h_ready, lane);
+      }
+    } else if (R == 32) {
       // ---- replicated mode: the 32 utterances of the tile occupy all four 32-row quarters of the M = 128 operand
       // (the same h rows four times), so all 16 epilogue warps share the cell updates: thread (quarter q, column
       // set cs, lane) owns utterance `lane` and the 4 hidden units (cs*4 + q)*4.. of every chunk; its cell state
@@ -191,16 +285,20 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
         const int grow = off2 + tt;
         const long gprow = poff2 + tt;
         uint8_t* hnew = himg + (size_t)((t + 1) & 1) * himg_bytes;
+        // input projection of this step, one chunk AHEAD of the cell update: the request for chunk c + 1 is in flight
+        // while chunk c waits for its accumulator, so no L2 latency sits between "accumulator ready" and the update
+        // (the epilogue is the longer pole of a step: two chunk epilogues against 2 x 1024 tensor cycles)
+        float gq[2][16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) gq[0][j] = gq[1][j] = 0.f;
+        if (active) load_gx16(p, grow, gprow, dir * 4 * H + 4 * usub, gq[0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c < nch) {
             const int ub = c * 64 + usub;
             const int col = dir * 4 * H + 4 * ub;              // gate-interleaved column of unit ub, gate i
-            float gq[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) gq[j] = 0.f;
             if (active) {
-              load_gx16(p, grow, gprow, col, gq);
+              if (c + 1 < nch) load_gx16(p, grow, gprow, col + 4 * 64, gq[(c + 1) & 1]);
               if (t + 1 < len2 && (p.gx_blk || (usub & 15) == 0))   // pull the next step's gx into L2
                 prefetch_gx16(p, grow + (dir == 0 ? 1 : -1), gprow + (dir == 0 ? 1 : -1), col);
             }
@@ -211,8 +309,8 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
             tmem_ld16(lane_addr + buf * 256u + (uint32_t)(usub * 4), v);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float ig = sigmoid_fast(v[4 * j] + gq[4 * j]), fg = sigmoid_fast(v[4 * j + 1] + gq[4 * j + 1]);
-              const float cg = tanh_fast(v[4 * j + 2] + gq[4 * j + 2]), og = sigmoid_fast(v[4 * j + 3] + gq[4 * j + 3]);
+              const float ig = sigmoid_fast(v[4 * j] + gq[c & 1][4 * j]), fg = sigmoid_fast(v[4 * j + 1] + gq[c & 1][4 * j + 1]);
+              const float cg = tanh_fast(v[4 * j + 2] + gq[c & 1][4 * j + 2]), og = sigmoid_fast(v[4 * j + 3] + gq[c & 1][4 * j + 3]);
               const float cn = fmaf(fg, creg[c][j], ig * cg);
               hf[j] = active ? og * tanh_fast(cn) : 0.f;
               if (active) creg[c][j] = cn;
