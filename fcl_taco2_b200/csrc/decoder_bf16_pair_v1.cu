@@ -605,8 +605,9 @@ decoder_bf16_pair_v1_kernel(FclDecoderBf16ParamsEx p) {
             const int u0 = c * 64 + cs * 16;                          // first of this thread's 16 hidden units
             // old cell state / old z of this chunk: requested BEFORE waiting for the accumulator (their L2 latency hides
             // behind the MMAs when the tensor pipe is the longer pole). No second register set for the next chunk: at 96
-            // registers per thread it is spilled (tried twice: a second set, and re-loading each 4-unit group's registers
-            // for the next chunk as soon as the group is done -- 280 B of spills, 1.80 -> 2.19 ms).
+            // registers per thread it is spilled (tried three times: a second set; re-loading each 4-unit group's registers
+            // for the next chunk as soon as the group is done -- 280 B of spills, 1.80 -> 2.19 ms; the same 2 units at a
+            // time with 8-column TMEM loads -- 64 B of spills, 1.73 -> 1.76 ms).
 #pragma unroll
             for (int j = 0; j < 16; ++j) c_cur[j] = (m == 0 || wi_noc || wi_skel) ? 0.f : __ldcg(cl + (size_t)(u0 + j) * 128 + r);
             if (!wi_skel) {
