@@ -311,6 +311,7 @@ decoder_bf16_pair_v1_kernel(FclDecoderBf16ParamsEx p) {
   const uint32_t b_bytes_wide = 128u * 64u * 2u, b_bytes_feat = 64u * 64u * 2u;
 
   // Register budget (see decoder_bf16.cu): warps 0-3 give up 32 registers per thread, the epilogue threads get 16 more.
+  // (104 is the most the pool gives: 112 compiles with 16 B of spills instead of 28 B but setmaxnreg.inc never returns.)
   // Each setmaxnreg has to dominate the code it is meant for, hence the two-level role dispatch.
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
