@@ -182,6 +182,10 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
     for (int kc = cs; kc < H / 8; kc += 4) *reinterpret_cast<uint4*>(himg + ((size_t)kc * 128 + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
     warp_arrive1(&sh.h_ready, lane);
+    // The zeroes above and the h rows written into the same image from step 1 on come from different threads. They are
+    // ordered through the issuer (h_ready -> MMAs -> tcgen05.commit -> tmem_full), a path compute-sanitizer's racecheck
+    // does not model; one named barrier among the epilogue warps makes the order explicit (once per kernel).
+    asm volatile("bar.sync 1, 512;" ::: "memory");
 
     if (R == 32 && (nch & 1) == 0) {
       // ---- replicated + split mode (even chunk counts: H = 128, 256). As below the 32 utterances of the tile occupy all
