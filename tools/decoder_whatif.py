@@ -49,6 +49,6 @@ cases = [("baseline", 0), ("L2 prefetch of the next chunk's cell state", 1 << 21
          ("all four", NOA | NOC | NOIMG | NOPHILOX)]
 for kern in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["v1"]):
     print(f"== {kern} ({kind} batch {batch}), decoder ms per launch (median of 6)")
-    for name, bits in cases + ([("ring 3 slots", ring(3)), ("ring 4 slots", ring(4)), ("ring 3 slots, no A", ring(3) | NOA)] if kern == "v1" else []):
+    for name, bits in cases + ([("ring 5 slots", ring(5)), ("ring 3 slots", ring(3)), ("ring 4 slots", ring(4)), ("ring 3 slots, no A", ring(3) | NOA)] if kern == "v1" else []):
         print(f"   {name:32s} {time_decoder(kern, bits):.3f}")
 eng.pair_kernel, eng.pair_inflight = "v1", 2
