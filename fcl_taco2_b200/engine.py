@@ -583,18 +583,34 @@ class Engine:
         for k, a in parts:
             offs[k] = (total, a.shape[0])
             total += (a.shape[0] + 3) // 4 * 4          # keep 16-byte alignment
-        if getattr(self, "_stage_buf", None) is None or self._stage_buf.numel() < total:
-            self._stage_buf = torch.empty((max(total, 1 << 16),), dtype=torch.int32).pin_memory()   # cached: pinning is slow
-        if getattr(self, "_stage_evt", None) is not None:
-            self._stage_evt.synchronize()               # the previous H2D copy out of this buffer has finished
-        stage = self._stage_buf[:total]
+        # Two pinned staging buffers and a dedicated upload stream: the H2D copy of batch i+1 runs while batch i computes
+        # (on the launching stream it sat between two passes: ~0.1 ms of idle GPU per batch), and refilling a staging
+        # buffer only waits for the copy that used it two uploads ago.
+        slot = getattr(self, "_stage_slot", 0)
+        self._stage_slot = slot ^ 1
+        bufs = getattr(self, "_stage_bufs", None)
+        if bufs is None:
+            bufs = self._stage_bufs = [None, None]
+            self._stage_evts = [None, None]
+            self._up_stream = torch.cuda.Stream(device=self.device)
+        if bufs[slot] is None or bufs[slot].numel() < total:
+            bufs[slot] = torch.empty((max(total, 1 << 16),), dtype=torch.int32).pin_memory()   # cached: pinning is slow
+            self._stage_evts[slot] = None
+        if self._stage_evts[slot] is not None:
+            self._stage_evts[slot].synchronize()        # the H2D copy that last read this buffer has finished
+        stage = bufs[slot][:total]
         sn = stage.numpy()
         for k, a in parts:
             o, n = offs[k]
             sn[o:o + n] = a
-        dev = stage.to(self.device, non_blocking=True)
-        self._stage_evt = torch.cuda.Event()
-        self._stage_evt.record(torch.cuda.current_stream(self.device))
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._up_stream):
+            dev = stage.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._up_stream)
+        self._stage_evts[slot] = ev
+        main.wait_event(ev)                             # the pass starts when its inputs have landed
+        dev.record_stream(main)                         # allocated on the upload stream, used on the launching stream
         v = {k: dev[o:o + n] for k, (o, n) in offs.items()}
         v["ids"] = v["ids"].view(torch.int64)
         for k in ("pitch", "energy"):
