@@ -5,8 +5,8 @@ import json, subprocess, sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 points = [("S", b, False) for b in (1, 8, 64, 256, 1024, 4096)] + [("T", b, False) for b in (1, 32, 256, 1024)] + \
          [("S", 64, True), ("T", 16, True)]
-print("# batch-size sweep, one B200, bf16 tensor-core path (bench.py --steps 5 --warmup 3; device-resident / end-to-end)\n")
-print("| model | batch | workload | frames/step | ms/step | M frames/s | e2e M frames/s | decoder ms | decoder frac of 1408.6 TF |")
+print("# batch-size sweep, one B200, 16-bit tensor-core path (bench.py --steps 5 --warmup 3; device-resident / end-to-end)\n")
+print("| model | batch | workload | frames/step | ms/step | M frames/s | e2e M frames/s | decoder ms | decoder frac of the burst tensor peak |")
 print("|---|---:|---|---:|---:|---:|---:|---:|---:|")
 for model, batch, stress in points:
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--model", model, "--batch", str(batch), "--steps", "5",
