@@ -283,8 +283,14 @@ def time_arm(arm, steps, warmup, dropout, flush, dist=None, dev=None, gather=Non
         return res, se
 
     import gc
+    # the warm-up keeps the previous result alive while the next pass runs, exactly like the timed loop below: the
+    # caching allocator then owns BOTH output blocks (185 MB each) before the bracket opens. Without this the second
+    # timed step found no free block and sat in cudaMalloc for several ms in the middle of the postnet launches (seen
+    # as a one-off 9 ms postnet stage in ~1 run out of 6).
+    wres = None
     for _ in range(warmup):
-        one_step(False)
+        wres, _se = one_step(False)
+    del wres
     if gather is not None:
         gather.drain()
     gc.collect()

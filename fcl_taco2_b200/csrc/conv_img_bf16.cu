@@ -31,13 +31,14 @@ using namespace umma;
 constexpr int kThreads = 640;
 constexpr int kEpiWarps = 16;
 constexpr int kMaxStages = 8;
+constexpr int kMaxResident = 16;                  // weight stages of a layer kept resident (b_resident mode)
 constexpr uint32_t kSlab = 136u * 16u;            // one 8-channel slab of a window: 136 rows x 16 B
 constexpr uint32_t kABytes = 8u * kSlab;          // one A stage: 64 channels
 constexpr int kRowOff = 4;                        // stored row = padded row + 4
 
 struct Shared {
   uint64_t a_full[kMaxStages], a_empty[kMaxStages];
-  uint64_t b_full[kMaxStages], b_empty[kMaxStages];
+  uint64_t b_full[kMaxResident], b_empty[kMaxStages];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
   alignas(16) float ln_part[2][4][128][2];        // [tile parity][column quarter][row][sum, sum of squares]
@@ -118,11 +119,13 @@ __device__ __forceinline__ float act_t(float x) {
 template <int EPI, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap, FclConvImgParams p,
-                int a_stages, int b_stages, int n_pairs) {
+                int a_stages, int b_stages, int n_pairs, int b_resident) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Shared sh;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) ci_trace(p, 1);                         // kernel entry
+  // per-CTA life span (%globaltimer, ns) behind the event records: records [trace_cap + blockIdx] = {entry, exit}
+  if (p.trace && tid == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); p.trace[2 + 2 * ((long long)p.trace_cap + blockIdx.x)] = (long long)g; }
   const uint32_t rank = cluster_ctarank();
   const int pair = (int)blockIdx.x >> 1;
   const int taps = p.taps, halo = taps >> 1, nb = p.nb;
@@ -142,7 +145,7 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
 
   if (tid == 0) {
     for (int s = 0; s < a_stages; ++s) { mbar_init(&sh.a_full[s], 1); mbar_init(&sh.a_empty[s], 1); }
-    for (int s = 0; s < b_stages; ++s) { mbar_init(&sh.b_full[s], 1); mbar_init(&sh.b_empty[s], 1); }
+    for (int s = 0; s < b_stages; ++s) { mbar_init(&sh.b_full[s], 1); if (s < kMaxStages) mbar_init(&sh.b_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&sh.tmem_full[b], 1); mbar_init(&sh.tmem_empty[b], 2 * kEpiWarps); }
     fence_barrier_init();
     prefetch_tmap(&amap);
@@ -166,7 +169,29 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
 
   if (warp == 0) {
     // ================================================================ TMA producer (both CTAs)
-    if (elect_one()) {
+    if (b_resident && elect_one()) {
+      // RESIDENT WEIGHTS (one N block, all kchunks * taps weight stages of the layer fit beside the window ring: the
+      // postnet layers, 80 KB per CTA): loaded once, every tile re-reads them in place. No weight traffic after the
+      // first tile, no weight barriers in the MMA issuer's loop, and the window ring gets the remaining shared memory
+      // (three tiles of windows in flight).
+      if (pair < n_super) {
+        for (int i = 0; i < kchunks * taps; ++i) {
+          if (rank == 0) mbar_arrive_expect_tx(&sh.b_full[i], 2u * b_bytes);
+          tma_load_2d_2sm(b_ring + (size_t)i * b_bytes, &wmap, mapa_u32(&sh.b_full[i], 0), 0, (i * 2 + (int)rank) * (nb / 4));
+        }
+      }
+      uint32_t a_ctr = 0;
+      for (int st = pair; st < n_super; st += n_pairs) {
+        const int tile = 2 * st + (int)rank;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          const uint32_t s = a_ctr % (uint32_t)a_stages, ph = (a_ctr / (uint32_t)a_stages) & 1u;
+          mbar_wait(&sh.a_empty[s], ph ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(&sh.a_full[s], 2u * kABytes);
+          tma_load_3d_2sm(a_ring + (size_t)s * kABytes, &amap, mapa_u32(&sh.a_full[s], 0), 0, tile * 16, kc * 8);
+          ++a_ctr;
+        }
+      }
+    } else if (!b_resident && elect_one()) {
       uint32_t a_ctr = 0, b_ctr = 0;
       for (int st = pair; st < n_super; st += n_pairs) {
         const int tile = 2 * st + (int)rank;            // an odd tile count leaves the last peer a tile past the end: TMA zero-fills
@@ -194,7 +219,66 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     // ================================================================ MMA issuer (leader CTA only)
-    if (rank == 0 && elect_one()) {
+    if (b_resident && rank == 0 && elect_one()) {
+      // resident weights: nblk == 1, accumulators double-buffered (launcher guarantees acc_cols <= 256).
+      // This thread's instruction chain is what bounds the layer: tools/mma_floor.cu measures 64 cycles per dependent
+      // M = 256, N = 128 MMA from a lean issue loop (52 for N = 64, 129 for N = 256) -- there is no 128-cycle floor in
+      // the pipe, the loops of round 2 simply took >= 120 cycles per MMA to issue. Hence: descriptors as
+      // (constant high word, low word = one add), the first tile (weights still landing) peeled off, everything that
+      // is loop-invariant hoisted.
+      uint32_t a_ctr = 0, acc_ctr = 0;
+      const uint32_t idesc = idesc_op_f32(256u, (uint32_t)nb);
+      const uint32_t b_fld = ((uint32_t)(nb / 2)) << 16, b_kstep = (uint32_t)nb;       // LBO field, K = 16 step (>> 4)
+      const uint32_t b_lo0 = (smem_u32(b_ring) >> 4) | b_fld, b_stage16 = b_bytes >> 4;
+      const uint32_t a_ring_lo = (smem_u32(a_ring) >> 4) + (uint32_t)(kRowOff - halo), a_fld = (kSlab >> 4) << 16;
+      constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+      constexpr uint32_t kAStep = (2u * kSlab) >> 4;
+      for (int st = pair; st < n_super; st += n_pairs) {
+        const uint32_t buf = acc_ctr & 1u, use = acc_ctr >> 1;
+        mbar_wait(&sh.tmem_empty[buf], (use & 1u) ^ 1u);
+        tc_fence_after();
+        ci_trace(p, 100);
+        const uint32_t d_tmem = tmem + buf * 256u;
+        uint32_t acc = 0u, b_lo = b_lo0;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          const uint32_t sa = a_ctr % (uint32_t)a_stages;
+          mbar_wait(&sh.a_full[sa], (a_ctr / (uint32_t)a_stages) & 1u);
+          tc_fence_after();
+          uint32_t a_lo = (a_ring_lo + sa * (kABytes >> 4)) | a_fld;
+          if (st == pair) {                              // first tile of this pair: the weights are still landing
+            for (int t = 0; t < taps; ++t) {
+              mbar_wait(&sh.b_full[kc * taps + t], 0u);
+              tc_fence_after();
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                mma2_bf16_ss(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + (uint32_t)k * kAStep),
+                             ((uint64_t)kDescHi << 32) | (b_lo + (uint32_t)k * b_kstep), idesc, acc);
+                acc = 1u;
+              }
+              a_lo += 1u;                                // next tap: one row (16 bytes) further
+              b_lo += b_stage16;
+            }
+          } else {
+#pragma unroll 1
+            for (int t = 0; t < taps; ++t) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                mma2_bf16_ss(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + (uint32_t)k * kAStep),
+                             ((uint64_t)kDescHi << 32) | (b_lo + (uint32_t)k * b_kstep), idesc, acc);
+                acc = 1u;
+              }
+              a_lo += 1u;
+              b_lo += b_stage16;
+            }
+          }
+          mma2_commit(&sh.a_empty[sa]);
+          ++a_ctr;
+        }
+        mma2_commit(&sh.tmem_full[buf]);
+        ci_trace(p, 200);
+        ++acc_ctr;
+      }
+    } else if (!b_resident && rank == 0 && elect_one()) {
       uint32_t a_ctr = 0, b_ctr = 0, acc_ctr = 0;
       const uint32_t idesc = idesc_op_f32(256u, (uint32_t)nb);
       const uint32_t b_lbo = (uint32_t)(nb / 2) * 16u;
@@ -450,6 +534,7 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
   cluster_sync_all();                                   // the leader's MMAs read the peer's shared memory: leave together
   if (warp == 2) tmem_dealloc2(tmem, 512);
   if (tid == 0) ci_trace(p, 4);                         // exit
+  if (p.trace && tid == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); p.trace[3 + 2 * ((long long)p.trace_cap + blockIdx.x)] = (long long)g; }
 }
 
 // ---------------------------------------------------------------- padded row space
@@ -597,8 +682,20 @@ extern "C" int fcl_conv_img_bf16(const FclConvImgParams* p, void* stream) {
   int b_stages = (int)((budget - (size_t)a_stages * kABytes) / b_bytes);
   if (b_stages > kMaxStages) b_stages = kMaxStages;
   FCL_REQUIRE(b_stages >= 2, "shared memory budget exceeded");
+  // resident weights (see the kernel): one N block of at most 256 columns whose kchunks * taps stages all fit
+  const int total_b = kchunks * p->taps;
+  const bool ln_epi = p->epi == FCL_EPI_LN_IMAGE || p->epi == FCL_EPI_LN_HEAD;
+  int b_resident = 0;
+  if (nblk == 1 && !ln_epi && p->nb <= 256 && total_b >= 2 && total_b <= kMaxResident &&
+      (size_t)total_b * b_bytes + (size_t)a_stages * kABytes <= budget) {
+    b_resident = 1;
+    b_stages = total_b;
+    a_stages = (int)((budget - (size_t)total_b * b_bytes) / kABytes);
+    if (a_stages > 3 * kchunks) a_stages = 3 * kchunks;        // three tiles of windows in flight
+    if (a_stages > kMaxStages) a_stages = kMaxStages;
+  }
   const size_t smem = (size_t)a_stages * kABytes + (size_t)b_stages * b_bytes + 1024;      // + alignment slack
-  typedef void (*Kern)(const CUtensorMap, const CUtensorMap, FclConvImgParams, int, int, int);
+  typedef void (*Kern)(const CUtensorMap, const CUtensorMap, FclConvImgParams, int, int, int, int);
   Kern kern = nullptr;
   const int act = p->act;
   if (p->epi == FCL_EPI_IMAGE) kern = act == FCL_ACT_RELU ? conv_img_kernel<FCL_EPI_IMAGE, FCL_ACT_RELU> : act == FCL_ACT_TANH ? conv_img_kernel<FCL_EPI_IMAGE, FCL_ACT_TANH> : conv_img_kernel<FCL_EPI_IMAGE, FCL_ACT_NONE>;
@@ -625,7 +722,7 @@ extern "C" int fcl_conv_img_bf16(const FclConvImgParams* p, void* stream) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, amap, wmap, *p, a_stages, b_stages, n_pairs);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, amap, wmap, *p, a_stages, b_stages, n_pairs, b_resident);
   if (e != cudaSuccess) { set_error("fcl_conv_img_bf16: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
   return check_launch("fcl_conv_img_bf16");
 }
