@@ -279,9 +279,14 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
         ++acc_ctr;
       }
     } else if (!b_resident && rank == 0 && elect_one()) {
-      uint32_t a_ctr = 0, b_ctr = 0, acc_ctr = 0;
+      uint32_t a_ctr = 0, acc_ctr = 0;
+      uint32_t sb = 0, sb_par = 0;                       // weight ring position / parity
       const uint32_t idesc = idesc_op_f32(256u, (uint32_t)nb);
-      const uint32_t b_lbo = (uint32_t)(nb / 2) * 16u;
+      const uint32_t b_fld = ((uint32_t)(nb / 2)) << 16, b_kstep = (uint32_t)nb;       // LBO field, K = 16 step (>> 4)
+      const uint32_t b_ring_lo = smem_u32(b_ring) >> 4, b_stage16 = b_bytes >> 4;
+      const uint32_t a_ring_lo = (smem_u32(a_ring) >> 4) + (uint32_t)(kRowOff - halo), a_fld = (kSlab >> 4) << 16;
+      constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+      constexpr uint32_t kAStep = (2u * kSlab) >> 4;
       for (int st = pair; st < n_super; st += n_pairs) {
         const uint32_t a_base = a_ctr;
         for (int blk = 0; blk < nblk; ++blk) {
@@ -299,20 +304,23 @@ conv_img_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
               mbar_wait(&sh.a_full[sa], ((a_base + (uint32_t)kc) / (uint32_t)a_stages) & 1u);
               tc_fence_after();
             }
-            const uint32_t a_addr = smem_u32(a_ring + (size_t)sa * kABytes);
+            // descriptors: constant high word, low word = (address >> 4) | (LBO >> 4) << 16 advanced by adds (see the
+            // resident loop above: this thread's instruction chain per MMA is what bounds the N < 256 layers)
+            uint32_t a_lo = ((a_ring_lo + sa * (kABytes >> 4)) | a_fld);
+            uint32_t acc = kc > 0 ? 1u : 0u;
             for (int t = 0; t < taps; ++t) {
-              const uint32_t sb = b_ctr % (uint32_t)b_stages;
-              mbar_wait(&sh.b_full[sb], (b_ctr / (uint32_t)b_stages) & 1u);
+              mbar_wait(&sh.b_full[sb], sb_par);
               tc_fence_after();
-              const uint32_t b_addr = smem_u32(b_ring + (size_t)sb * b_bytes);
+              const uint32_t b_lo = (b_ring_lo + sb * b_stage16) | b_fld;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = smem_desc(a_addr + (uint32_t)(kRowOff - halo + t) * 16u + (uint32_t)k * 2u * kSlab, kSlab, 128u);
-                const uint64_t bd = smem_desc(b_addr + (uint32_t)k * 2u * b_lbo, b_lbo, 128u);
-                mma2_bf16_ss(d_tmem, ad, bd, idesc, (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
+                mma2_bf16_ss(d_tmem, ((uint64_t)kDescHi << 32) | (a_lo + (uint32_t)k * kAStep),
+                             ((uint64_t)kDescHi << 32) | (b_lo + (uint32_t)k * b_kstep), idesc, acc);
+                acc = 1u;
               }
+              a_lo += 1u;                               // next tap: one row (16 bytes) further
               mma2_commit(&sh.b_empty[sb]);             // frees the weight stage in BOTH CTAs
-              ++b_ctr;
+              if (++sb == (uint32_t)b_stages) { sb = 0; sb_par ^= 1u; }
             }
             if (blk == nblk - 1) mma2_commit(&sh.a_empty[sa]);     // the window stage is free once the last N block used it
           }
@@ -686,7 +694,7 @@ extern "C" int fcl_conv_img_bf16(const FclConvImgParams* p, void* stream) {
   const int total_b = kchunks * p->taps;
   const bool ln_epi = p->epi == FCL_EPI_LN_IMAGE || p->epi == FCL_EPI_LN_HEAD;
   int b_resident = 0;
-  if (nblk == 1 && !ln_epi && p->nb <= 256 && total_b >= 2 && total_b <= kMaxResident &&
+  if (nblk == 1 && !ln_epi && p->epi != FCL_EPI_ROWS_F32 && p->nb <= 256 && total_b >= 2 && total_b <= kMaxResident &&
       (size_t)total_b * b_bytes + (size_t)a_stages * kABytes <= budget) {
     b_resident = 1;
     b_stages = total_b;
