@@ -95,6 +95,10 @@ def test_pad_rows_and_rows_to_image():
     (1500, 512, 512, 5),         # T encoder conv: two N blocks re-read the resident window (8 A stages)
     (1000, 384, 128, 3),         # nb = 128
     (1000, 64, 192, 1),          # one K stage, nb = 192, plain linear
+    (600 * 128, 128, 128, 5),    # postnet-sized layer: RESIDENT weights (10 stages), ~4 super-tiles per pair, 6 window stages
+    (1000, 128, 128, 5),         # resident weights, fewer tiles than CTA pairs
+    (90, 128, 128, 3),           # resident weights, one tile (the peer's tile is past the end)
+    (3000, 64, 128, 5),          # resident weights, one K chunk per tile (3 window stages)
 ])
 def test_conv_img_image_epilogue(total, cin, cout, taps):
     rs = np.random.RandomState(total + cin)
