@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # FCL_TACO2_LIB selects another build of the same library (tools: the -DFCL_DEC_PROF profiling build)
 LIB_PATH = os.environ.get("FCL_TACO2_LIB") or os.path.join(_HERE, "lib", "libfcl_taco2.so")
-ABI_VERSION = 28
+ABI_VERSION = 29
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
 ptr = C.c_void_p
@@ -165,7 +165,7 @@ ENTRY_POINTS = {
     "fcl_conv_img_bf16": ConvImgParams,
     "fcl_prenet0_tf": Prenet0TfParams,
 }
-PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_l2_persist_limit", "fcl_operand_format", "fcl_last_error", "fcl_sm_count", "fcl_struct_size",
+PLAIN_SYMBOLS = ["fcl_abi_version", "fcl_operand_format", "fcl_last_error", "fcl_sm_count", "fcl_struct_size",
                  "fcl_decoder_bf16_workspace", "fcl_len_reg_ws_ints", "fcl_peer_alloc", "fcl_peer_free", "fcl_ipc_export", "fcl_ipc_open",
                  "fcl_ipc_close", "fcl_copy_async", "fcl_wait_flags", "fcl_write_flags"]
 
@@ -207,8 +207,6 @@ def load():
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(st), C.c_void_p]
-    lib.fcl_l2_persist_limit.restype = C.c_int
-    lib.fcl_l2_persist_limit.argtypes = [C.c_int64, C.POINTER(C.c_int64)]
     lib.fcl_len_reg_ws_ints.restype = C.c_int
     lib.fcl_len_reg_ws_ints.argtypes = [C.c_int32]
     lib.fcl_decoder_bf16_workspace.restype = C.c_int
@@ -251,14 +249,6 @@ def operand_format() -> str:
 def dptr(t):
     """Device pointer of a torch tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
-
-
-def l2_persist_limit(nbytes: int) -> int:
-    """Configure the L2 set-aside for persisting accesses on the current device; returns the size actually set."""
-    got = C.c_int64(0)
-    if load().fcl_l2_persist_limit(int(nbytes), C.byref(got)) != 0:
-        raise FclError(f"fcl_l2_persist_limit failed: {load().fcl_last_error().decode()}")
-    return int(got.value)
 
 
 def decoder_bf16_workspace(prenet_units: int, dunits: int):

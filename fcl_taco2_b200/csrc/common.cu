@@ -40,30 +40,6 @@ extern "C" int fcl_sm_count(void) {
   return n;
 }
 
-// L2 set-aside for persisting accesses on the current device (cudaLimitPersistingL2CacheSize, clamped to the device
-// maximum). Kernels that mark a window persisting (the pair decoder's cell-state scratch) do so per launch and demote
-// their lines before they exit, so other kernels see the whole L2; without a set-aside the windows have no effect.
-namespace fcl { static size_t g_l2_persist[64] = {0}; size_t l2_persist_bytes() { int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0; return g_l2_persist[dev]; } }
-extern "C" int fcl_l2_persist_limit(int64_t bytes, int64_t* set_bytes) {
-  int dev = 0, maxb = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&maxb, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess) {
-    fcl::set_error("fcl_l2_persist_limit: %s", cudaGetErrorString(cudaGetLastError()));
-    return FCL_ECUDA;
-  }
-  size_t want = bytes < 0 ? 0 : (size_t)bytes;
-  if (want > (size_t)maxb) want = (size_t)maxb;
-  if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
-    fcl::set_error("fcl_l2_persist_limit: %s", cudaGetErrorString(cudaGetLastError()));
-    return FCL_ECUDA;
-  }
-  size_t got = 0;
-  cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
-  if (dev >= 0 && dev < 64) fcl::g_l2_persist[dev] = got;
-  if (set_bytes) *set_bytes = (int64_t)got;
-  return FCL_OK;
-}
-
 // ABI self-check for foreign-language bindings: sizeof of every parameter struct.
 extern "C" int fcl_struct_size(int which) {
   switch (which) {

@@ -9,7 +9,6 @@ namespace fcl {
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
-size_t l2_persist_bytes();       // L2 set-aside configured on the current device by fcl_l2_persist_limit (0 = none)
 
 #define FCL_REQUIRE(cond, msg)                                                   \
   do {                                                                           \

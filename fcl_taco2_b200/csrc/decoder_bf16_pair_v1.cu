@@ -50,7 +50,6 @@ constexpr int kDbMaxTilesPerCta = 512;
 // kernel-side parameters: the C-ABI struct plus launcher-derived switches
 struct FclDecoderBf16ParamsEx : FclDecoderBf16Params {
   int smem_consts;            // epilogue constants staged in shared memory behind the ring (they fit)
-  int c_persist;              // c_ws is an L2-persisting access-policy window of this launch: demote the lines at the end
 };
 
 struct DbShared {
@@ -748,13 +747,6 @@ decoder_bf16_pair_v1_kernel(FclDecoderBf16ParamsEx p) {
   tc_fence_before();
   cluster_sync_all();                                   // the leader's MMAs read the peer's shared memory: leave together
   if (warp == 2) tmem_dealloc2(tmem, 512);
-  // The launcher marks the cell-state scratch as an L2-persisting window (below). Hand the lines back: the kernels that
-  // follow (postnet) want the whole L2 (round 1 measured +11 % on the postnet with the lines left persisting).
-  if (p.c_persist) {
-    const char* base = reinterpret_cast<const char*>(cws);
-    for (uint32_t off = (uint32_t)tid * 128u; off < (uint32_t)(2 * H * 128 * 4); off += kDbThreads * 128u)
-      asm volatile("applypriority.global.L2::evict_normal [%0], 128;" ::"l"(base + off));
-  }
 #ifdef FCL_DEC_PROF
   if (DB_PROF_ON(p) && tid < 48) p.trace[tid] = sh.prof[tid];
 #endif
@@ -799,30 +791,11 @@ extern "C" int fcl_decoder_bf16_pair_v1(const FclDecoderBf16Params* p, void* str
   cfg.blockDim = dim3(kDbThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = as_stream(stream);
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  // The fp32 cell state (256 KB per CTA, 38 MB for 148 CTAs) is written at step m and read back at step m + 1 after
-  // ~4 MB of other traffic per SM went through L2: without help every line is evicted to DRAM and fetched again
-  // (2.4 GB written + 1 GB read per launch, profiles/r02_kernels_ncu.md). With an L2 set-aside configured
-  // (fcl_l2_persist_limit) the scratch is marked persisting for this launch only.
-  const size_t c_bytes = (size_t)p->n_slots * 2 * p->dunits * 128 * sizeof(float);
-  px.c_persist = 0;
-  if (l2_persist_bytes() >= c_bytes) {
-    attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
-    attr[1].val.accessPolicyWindow.base_ptr = p->c_ws;
-    attr[1].val.accessPolicyWindow.num_bytes = c_bytes;
-    attr[1].val.accessPolicyWindow.hitRatio = 1.0f;
-    attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-    cfg.numAttrs = 2;
-    px.c_persist = 1;
-  }
-#ifdef FCL_DEC_PROF
-  if ((p->inflight >> 25) & 1) { cfg.numAttrs = 1; px.c_persist = 0; }   // what-if: no persisting window
-#endif
   cudaError_t e = cudaLaunchKernelEx(&cfg, decoder_bf16_pair_v1_kernel, px);
   if (e != cudaSuccess) { set_error("fcl_decoder_bf16_pair_v1: %s", cudaGetErrorString(e)); return FCL_ECUDA; }
   return check_launch("fcl_decoder_bf16_pair_v1");

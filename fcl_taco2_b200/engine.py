@@ -61,8 +61,6 @@ class Engine:
         with torch.cuda.device(self.device):      # fcl_sm_count() and the kernels' per-device attributes use the CURRENT device
             self._init_device_state(hp, packed, precision, bf16_gemms, bf16_decoder)
 
-    use_l2_persist = True            # class-level switch (tests / A-B runs): configure the L2 set-aside for the decoder
-
     def _init_device_state(self, hp, packed, precision, bf16_gemms, bf16_decoder):
         self.w = {k: v.to(self.device) for k, v in packed.items()}
         self.wb = {}
@@ -89,9 +87,6 @@ class Engine:
             self.dec_act_shared = torch.empty((self.n_slots * shared_b,), dtype=torch.uint8, device=self.device)
             self.dec_c_ws = torch.empty((2 * self.n_slots * c_f,), dtype=torch.float32, device=self.device)
             self.dec_group_sync = torch.zeros((2 * self.n_slots,), dtype=torch.int32, device=self.device)
-            # L2 set-aside that lets the pair decoder keep its fp32 cell state (n_slots x c_f floats) resident between
-            # steps; the kernel demotes the lines before it exits. 0 / unsupported: the decoder runs without the window.
-            self.l2_persist = _lib.l2_persist_limit(self.n_slots * c_f * 4) if self.use_l2_persist else 0
         self.head_b = {s: float(packed[f"{s}_head_b"][0]) for s in ("dur", "pitch", "energy")}
         self.launches = 0
         self._arena, self._arena_views, self._arena_seq, self._in_pass = [], [], 0, False

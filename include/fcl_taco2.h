@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FCL_ABI_VERSION 28
+#define FCL_ABI_VERSION 29
 
 enum {
   FCL_OK = 0,
@@ -39,12 +39,6 @@ enum {
 enum { FCL_ACT_NONE = 0, FCL_ACT_RELU = 1, FCL_ACT_TANH = 2 };
 
 int fcl_abi_version(void);
-/* L2 set-aside for persisting accesses on the current device (cudaLimitPersistingL2CacheSize; clamped to the device
- * maximum; 0 removes it); *set_bytes (optional) receives the size actually set. fcl_decoder_bf16_pair_v1 marks its fp32
- * cell-state scratch as a persisting access-policy window of the launch when the set-aside covers it, and demotes the
- * lines before it exits (the kernels that follow see the whole L2). No reference counterpart: the reference keeps the
- * LSTM state in framework tensors (decoder_sa.py:577-617). */
-int fcl_l2_persist_limit(int64_t bytes, int64_t* set_bytes);
 /* Element format of the 16-bit GEMM operands (weights packed by the host, activation images written by the kernels) of
  * every tensor-core entry point (the `_bf16` suffix of their names is historical): 0 = IEEE fp16 (default build: 11-bit
  * significand, conversions saturate at +-65504), 1 = bfloat16 (library built with -DFCL_OPERANDS_BF16). The host packs

@@ -40,7 +40,7 @@ def time_decoder(kern, bits, reps=6):
 SKEL, NOMATH, CNORMAL = 1 << 15, 1 << 16, 1 << 17
 ALU, SLEEP = 1 << 18, 1 << 19
 cases = [("baseline", 0), ("L2 prefetch of the next chunk's cell state", 1 << 21),
-         ("epilogue constants from global memory (as before)", 1 << 24), ("no L2-persisting window on the cell state", 1 << 25),
+         ("epilogue constants from global memory (as before)", 1 << 24),
          ("roles in the last 4 warps", 1 << 20), ("skeleton epilogue", SKEL),
          ("skeleton + 800 IMAD per thread-chunk", SKEL | ALU), ("skeleton + 3200 cycles asleep per chunk", SKEL | SLEEP), ("skeleton epilogue, no A", SKEL | NOA),
          ("no cell math (TMEM ld + stores)", NOMATH), ("no cell math, no Philox", NOMATH | NOPHILOX),
