@@ -10,7 +10,7 @@ m = M.from_preset("S", seed=0, device="cuda:0", precision="fp16").set_prenet_dro
 eng = m.engine()
 xs, ds = synth.synth_batch(1024, 0)
 pl = planmod.make_plan(xs, ds)
-for mp in (None, 37, 18, 9):
+for mp in [int(a) if a != "all" else None for a in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["all", "37", "18", "9"])]:
     eng.max_pairs = mp
     for _ in range(2):
         eng.run(pl, 0.1, 0.5, 1)
