@@ -562,7 +562,8 @@ class Engine:
 
     # ------------------------------------------------------------------ whole pass
     def upload(self, plan: BatchPlan):
-        """One pinned staging buffer, one H2D copy. -> dict of device views + byte count."""
+        """All inputs of a batch in one pinned staging buffer (two alternate), one H2D copy on the upload stream.
+        -> dict of device views + byte count."""
         P, B = plan.n_rows, plan.n_utts
         parts = [("ids", plan.ids.view(np.int32)), ("utt_off", plan.utt_off), ("row_utt", plan.row_utt),
                  ("row_phone", plan.row_phone), ("seg_lo", plan.seg_lo), ("seg_hi", plan.seg_hi)]
