@@ -60,11 +60,24 @@ __device__ __forceinline__ void warp_arrive1(uint64_t* bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
 
+// Counter-mode profile (profiling build -DFCL_DEC_PROF only, tools/bilstm_prof.py): CTA (0, 0) accumulates %clock deltas
+// and dumps them into the first words of c_ws (unused by the replicated modes): [0] steps, [1] issuer: waiting for
+// h_ready, [2] issuer: issuing a step, [3 + 2 * half] epilogue half: waiting for its accumulator, [4 + 2 * half] its body
+#ifdef FCL_DEC_PROF
+#define BL_PROF(idx) do { if (prof) { const uint32_t n_ = clk32b(); sh.prof[idx] += n_ - pt; pt = n_; } } while (0)
+__device__ __forceinline__ uint32_t clk32b() { uint32_t c; asm volatile("mov.u32 %0, %%clock;" : "=r"(c)); return c; }
+#else
+#define BL_PROF(idx) do { } while (0)
+#endif
+
 struct BlShared {
   uint64_t full[4], empty[4];
   uint64_t tmem_full[2], tmem_empty[2];
   uint64_t h_ready;
   uint32_t tmem_base;
+#ifdef FCL_DEC_PROF
+  uint32_t prof[8];
+#endif
 };
 
 __global__ void __launch_bounds__(kBlThreads, 1)
@@ -94,6 +107,9 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
     mbar_init(&sh.h_ready, kBlEpiThreads / 32);
     fence_barrier_init();
   }
+#ifdef FCL_DEC_PROF
+  if (tid < 8) sh.prof[tid] = 0u;
+#endif
   if (warp == 2) tmem_alloc(&sh.tmem_base, 512);
   tc_fence_before();
   __syncthreads();
@@ -131,9 +147,43 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
       constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
       constexpr uint32_t kALo = (2048u >> 4) << 16, kBLo = (4096u >> 4) << 16;
       const uint32_t ring_lo = smem_u32(smem) >> 4;
+#ifdef FCL_DEC_PROF
+      const bool prof = blockIdx.x == 0 && blockIdx.y == 0;
+      uint32_t pt = clk32b();
+#endif
+      if (resident && nch == 2 && kH == 2) {
+        // H = 128: 16 MMAs per step against resident weights, fully unrolled with immediate descriptor offsets. The
+        // profile (tools/bilstm_prof.py) showed this thread taking 144 cycles per MMA in the generic loop below: more
+        // than the 128 cycles the pipe needs, and all of it on the step's critical chain.
+        const uint32_t a0 = (smem_u32(himg) >> 4) + kALo, a_par = himg_bytes >> 4, b0 = ring_lo + kBLo;
+        for (int t = 0; t < steps; ++t) {
+          if (t == 0) {
+            for (int s2 = 0; s2 < 4; ++s2) mbar_wait(&sh.full[s2], 0u);
+          }
+          mbar_wait(&sh.h_ready, (uint32_t)t & 1u);
+          tc_fence_after();
+          BL_PROF(1);
+          const uint32_t a_lo = a0 + ((uint32_t)t & 1u) * a_par;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            mbar_wait(&sh.tmem_empty[c], ((uint32_t)t & 1u) ^ 1u);   // buffer c is used once per step
+            tc_fence_after();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {                    // i = ks * 4 + k
+              const uint64_t ad = ((uint64_t)kDescHi << 32) | (a_lo + (uint32_t)i * (4096u >> 4));
+              const uint64_t bd = ((uint64_t)kDescHi << 32) |
+                                  (b0 + (uint32_t)(c * 2 + (i >> 2)) * (kBlBBytes >> 4) + (uint32_t)(i & 3) * (8192u >> 4));
+              mma_bf16_ss(tmem + (uint32_t)c * 256u, ad, bd, idesc, i > 0 ? 1u : 0u);
+            }
+            mma_commit(&sh.tmem_full[c]);
+          }
+          BL_PROF(2);
+        }
+      } else
       for (int t = 0; t < steps; ++t) {
         mbar_wait(&sh.h_ready, (uint32_t)t & 1u);          // h(t-1) image complete (t = 0: zeros)
         tc_fence_after();
+        BL_PROF(1);
         uint32_t a_lo = (smem_u32(himg + (size_t)(t & 1) * himg_bytes) >> 4) + kALo;
         for (int c = 0; c < nch; ++c) {
           const uint32_t buf = chunk_ctr & 1u, use = chunk_ctr >> 1;
@@ -160,6 +210,7 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
           mma_commit(&sh.tmem_full[buf]);
           ++chunk_ctr;
         }
+        BL_PROF(2);
       }
     }
     __syncwarp();
@@ -209,6 +260,10 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) creg[c][j] = 0.f;
       uint32_t my_use = 0;                                   // uses of accumulator buffer `half` so far
+#ifdef FCL_DEC_PROF
+      const bool prof = blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 4 || warp == 12);
+      uint32_t pt = clk32b();
+#endif
       for (int t = 0; t < steps; ++t) {
         const bool active = t < len2;
         const int tt = dir == 0 ? t : len2 - 1 - t;
@@ -234,6 +289,7 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
             }
             mbar_wait(&sh.tmem_full[half], my_use & 1u);
             tc_fence_after();
+            BL_PROF(3 + 2 * half);
             float hf[8];
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
@@ -264,6 +320,7 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
         }
         fence_proxy_async_smem();
         warp_arrive1(&sh.h_ready, lane);
+        BL_PROF(4 + 2 * half);
       }
     } else if (R == 32) {
       // ---- replicated mode: the 32 utterances of the tile occupy all four 32-row quarters of the M = 128 operand
@@ -405,6 +462,9 @@ bilstm_bf16_kernel(FclBiLstmBf16Params p, int stages) {
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
+#ifdef FCL_DEC_PROF
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid < 8) reinterpret_cast<uint32_t*>(p.c_ws)[tid] = tid == 0 ? (uint32_t)steps : sh.prof[tid];
+#endif
 }
 
 }  // namespace fcl
