@@ -17,6 +17,11 @@
 // LEADER's mbarrier (.cta_group::2 form), so there is no relay thread and no remote "data landed" arrival at all.
 // The grid is persistent: pairs walk super-tiles; accumulators are double-buffered in TMEM when they are <= 256
 // columns wide, so the epilogue of one tile overlaps the MMAs of the next.
+// Round 2, second half: layers whose kchunks x taps weight stages all fit beside the window ring (the postnet: 80 KB per
+// CTA) keep their weights RESIDENT in shared memory (b_resident: loaded once per CTA, no weight barriers in the issue
+// loop, window ring three tiles deep), and the MMA issue loops build their descriptors with one add per MMA:
+// tools/mma_floor.cu shows the pipe needs 64 cycles per M = 256, N = 128 MMA (52 for N = 64, 129 for N = 256) -- the
+// ~128 cycles per MMA "whatever N" seen earlier was the issuing thread, not the pipe.
 // Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader), warp 2 = TMEM allocator,
 // warps 4-19 = epilogue (TMEM lane quarter = warp % 4 -> row; column quarter = (warp - 4) / 4).
 #include "common.cuh"
